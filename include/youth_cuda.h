@@ -1,0 +1,161 @@
+/*
+ * youth_cuda.h -- C ABI of libyouth_cuda.so, the B200 (sm_100a) dense frame-to-frame
+ * depth tracker that sits behind the AlgorithmModule facade (include/SLAM.h).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * What each entry point replaces in the reference:
+ *
+ *   youth_cuda_init          <- `new ORB_SLAM3::System(...)`        Youth.Source/AlgorithmModule/SLAM.cpp:78-83
+ *   youth_cuda_track[_batch] <- `slam_system->TrackRGBD(...)`       SLAM.cpp:54 (+ the int16->float metres
+ *                                                                   conversion of SLAM.cpp:133-134,153-155,
+ *                                                                   fused into the ingest kernel)
+ *   youth_cuda_get_trajectory<- `SaveTrajectoryTUM` pose egress     SLAM.cpp:187-188
+ *   youth_cuda_last_inliers  <- `GetAllMapPoints().size()`          SLAM.cpp:212-217
+ *   youth_cuda_reset         <- `slam_system->Reset()`              SLAM.cpp:226
+ *   youth_cuda_destroy       <- `slam_system->Shutdown()`           SLAM.cpp:110
+ *   back-projection formula  <- display_3d_color()                  Youth.Source/ViewerModule/viewerModule.c:341-345
+ *
+ * Return convention follows the facade (SLAM.h:21,26,30): 1 = success, 0 = failure;
+ * youth_cuda_last_error() returns a thread-local description of the last failure.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Numerical contract (frozen by oracle/youth_oracle.c): no
+ * fused multiply-add anywhere, IEEE division/sqrt, fixed-order reductions -- the
+ * device results are bit-identical to the CPU oracle.
+ */
+#ifndef YOUTH_CUDA_H
+#define YOUTH_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YOUTH_CUDA_ABI_VERSION 1
+#define YOUTH_MAX_LEVELS 4
+#define YOUTH_ICP_THREADS 256 /* threads per ICP tile (reduction geometry, part of the spec) */
+#define YOUTH_SUM_SLOTS 32    /* 21 JtJ + 6 Jtr + sum r^2 + inlier count + 3 spare */
+
+typedef struct youth_cuda_handle youth_cuda_handle;
+
+typedef struct youth_cuda_config {
+  int32_t width, height;  /* level-0 image size; both divisible by 2^(levels-1), width % 8 == 0 */
+  float fx, fy, cx, cy;   /* level-0 pinhole intrinsics (Camera.fx/fy/cx/cy)                  */
+  float depth_factor;     /* raw units per metre (DepthMapFactor, 1000 for Astra)             */
+  int32_t levels;         /* pyramid levels, 1..YOUTH_MAX_LEVELS                              */
+  int32_t iters[YOUTH_MAX_LEVELS]; /* ICP iterations per level, index = level (0 = finest)    */
+  int32_t depth_min_mm;   /* raw depth valid iff depth_min_mm <= d <= depth_max_mm            */
+  int32_t depth_max_mm;
+  int32_t bilateral;      /* 1: 7x7 bilateral filter on raw depth, 0: pass-through            */
+  float sigma_space_px;   /* bilateral spatial sigma (pixels)                                 */
+  float sigma_range_mm;   /* bilateral range sigma (raw units); pyramid gate = 3 sigma        */
+  float dist_thresh_m;    /* correspondence rejection: |T v - v'| > dist_thresh               */
+  float cos_thresh;       /* correspondence rejection: (R n) . n' < cos_thresh                */
+  int32_t min_inliers;    /* an iteration with fewer inliers leaves the pose unchanged        */
+  int32_t icp_ppt;        /* pixels per thread per ICP tile: 1, 2, 4 or 8 (tile = 256*ppt px) */
+  int32_t n_streams;      /* independent sequences tracked by this handle (>= 1)              */
+  int32_t batch;          /* max frames per sequence per youth_cuda_track_batch call (>= 1)   */
+  int32_t traj_capacity;  /* max poses kept per sequence                                      */
+  int32_t device;         /* CUDA device ordinal                                              */
+  void* stream;           /* cudaStream_t to launch on; NULL = library-owned stream           */
+} youth_cuda_config;
+
+/* where the depth frames handed to youth_cuda_track_batch live */
+#define YOUTH_MEM_HOST 0        /* pageable host memory: staged through a pinned buffer, copied before return */
+#define YOUTH_MEM_DEVICE 1      /* device memory on cfg.device: consumed in place                              */
+#define YOUTH_MEM_HOST_PINNED 2 /* page-locked host memory (youth_cuda_host_alloc): async H2D, caller keeps it
+                                   alive until the next youth_cuda_sync / blocking call                        */
+
+/* debug read-back selectors (parity tests) */
+#define YOUTH_DBG_DEPTH 1  /* float[h*w]    filtered / downsampled depth in raw units, 0 = invalid */
+#define YOUTH_DBG_VERTEX 2 /* float[h*w*4]  x,y,z,valid(1/0)                                      */
+#define YOUTH_DBG_NORMAL 3 /* float[h*w*4]  nx,ny,nz,valid(1/0)                                   */
+#define YOUTH_DBG_MASK 4   /* uint8[h*w]    bit0 vertex valid, bit1 normal valid                  */
+#define YOUTH_DBG_PYRCNT 5 /* uint8[h*w]    samples averaged by the pyramid (level >= 1)          */
+
+/* per-frame status bits (youth_cuda_get_status) */
+#define YOUTH_STATUS_FIRST 1u    /* first frame of a sequence: pose = identity, no ICP        */
+#define YOUTH_STATUS_LOST 2u     /* >= 1 iteration skipped (too few inliers / singular system) */
+
+/* Fill *cfg with the Astra defaults: 640x480, fx=fy=570.3, cx=320, cy=240, factor 1000
+ * (reference config/astra_orb_slam3_rgbd.yaml:9-20,35), 3 levels with 10/5/4 iterations
+ * (fine->coarse), bilateral on (7x7, 4.5 px, 30 mm), 0.10 m / cos 20 deg gates. */
+int youth_cuda_default_config(youth_cuda_config* cfg);
+
+int youth_cuda_init(const youth_cuda_config* cfg, youth_cuda_handle** out);
+void youth_cuda_destroy(youth_cuda_handle* h);
+
+/* Track ONE frame of sequence 0 (host memory, copied before return).  pose_out (nullable)
+ * receives the camera-to-world pose, row-major 3x4 [R|t], world = first camera frame;
+ * when it is NULL the call returns after enqueueing the work. */
+int youth_cuda_track(youth_cuda_handle* h, const uint16_t* depth_mm, uint32_t timestamp_ms,
+                     float pose_out[12]);
+
+/* Track n_frames (1..cfg.batch) consecutive frames of EVERY sequence in one launch group.
+ * depth[s] points at n_frames tightly packed frames of sequence s (mem_kind says where).
+ * timestamps_ms: [n_frames] shared by all sequences, nullable.  poses_out: nullable
+ * [n_streams][n_frames][12]; non-NULL makes the call blocking. */
+int youth_cuda_track_batch(youth_cuda_handle* h, const uint16_t* const* depth, int n_frames,
+                           int mem_kind, const uint32_t* timestamps_ms, float* poses_out);
+
+/* Block until everything enqueued on the handle has finished. */
+int youth_cuda_sync(youth_cuda_handle* h);
+
+/* Forget trajectory and previous frame of sequence `stream` (-1 = all). */
+int youth_cuda_reset(youth_cuda_handle* h, int stream);
+
+/* Number of frames tracked so far in sequence `stream`. */
+int youth_cuda_frame_count(youth_cuda_handle* h, int stream);
+
+/* Copy up to max_frames poses (12 floats each) / timestamps / status words of sequence
+ * `stream`, starting at frame `first`; returns the number copied (blocking), -1 on error. */
+int youth_cuda_get_trajectory(youth_cuda_handle* h, int stream, int first, int max_frames,
+                              float* poses_out, uint32_t* timestamps_out, uint32_t* status_out);
+
+/* Inlier correspondences of the last tracked frame of `stream` at the finest level
+ * (last iteration); blocking. */
+int youth_cuda_last_inliers(youth_cuda_handle* h, int stream);
+
+/* Device pointer of the trajectory of sequence `stream` (float[traj_capacity][12]) for
+ * zero-copy hand-off to a collective (NCCL gather of per-sequence trajectories). */
+void* youth_cuda_trajectory_device_ptr(youth_cuda_handle* h, int stream);
+
+/* Page-locked host memory for YOUTH_MEM_HOST_PINNED inputs. */
+void* youth_cuda_host_alloc(size_t bytes);
+void youth_cuda_host_free(void* p);
+
+/* Parity hooks.  `frame` is the absolute frame index inside the sequence; it must still
+ * be resident in the ring (the last cfg.batch+1 frames are). */
+int youth_cuda_debug_read(youth_cuda_handle* h, int what, int stream, int frame, int level,
+                          void* dst, size_t dst_bytes);
+/* One association + reduction pass (stage 3+4) of frame `frame` against frame-1 at `level`
+ * with the given prev<-cur pose; sums_out[YOUTH_SUM_SLOTS] (double), corr_out nullable
+ * int32[h*w]: matched pixel index in the previous frame, or a negative reject code. */
+int youth_cuda_debug_icp(youth_cuda_handle* h, int stream, int frame, int level,
+                         const float pose[12], double* sums_out, int32_t* corr_out);
+
+/* Elapsed device milliseconds between two marks on the handle's stream. */
+int youth_cuda_timer_start(youth_cuda_handle* h);
+int youth_cuda_timer_stop(youth_cuda_handle* h, float* ms_out);
+
+/* Kernels launched by this handle since init (for bench.py's gpu_launches). */
+uint64_t youth_cuda_launch_count(youth_cuda_handle* h);
+
+const char* youth_cuda_last_error(void);
+int youth_cuda_abi_version(void);
+
+/* correspondence reject codes written by youth_cuda_debug_icp */
+#define YOUTH_REJ_CUR_INVALID (-1)
+#define YOUTH_REJ_BEHIND (-2)
+#define YOUTH_REJ_OUT_OF_IMAGE (-3)
+#define YOUTH_REJ_PREV_INVALID (-4)
+#define YOUTH_REJ_DISTANCE (-5)
+#define YOUTH_REJ_ANGLE (-6)
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* YOUTH_CUDA_H */

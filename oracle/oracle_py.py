@@ -1,0 +1,180 @@
+"""ctypes view of the CPU oracle (oracle/youth_oracle.h).  TEST INFRASTRUCTURE ONLY: may be
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs -- never by anything under slam-rgbd_b200/."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MAX_LEVELS = 4
+SUM_SLOTS = 32
+
+
+class OracleConfig(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+        ("depth_factor", C.c_float),
+        ("levels", C.c_int32),
+        ("iters", C.c_int32 * MAX_LEVELS),
+        ("depth_min_mm", C.c_int32), ("depth_max_mm", C.c_int32),
+        ("bilateral", C.c_int32),
+        ("sigma_space_px", C.c_float), ("sigma_range_mm", C.c_float),
+        ("dist_thresh_m", C.c_float), ("cos_thresh", C.c_float),
+        ("min_inliers", C.c_int32),
+        ("icp_ppt", C.c_int32),
+    ]
+
+
+class Level(C.Structure):
+    _fields_ = [("w", C.c_int32), ("h", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float),
+                ("cy", C.c_float)]
+
+
+class Frame(C.Structure):
+    _fields_ = [("depth", C.POINTER(C.c_float) * MAX_LEVELS), ("pyrcnt", C.POINTER(C.c_uint8) * MAX_LEVELS),
+                ("vmap", C.POINTER(C.c_float) * MAX_LEVELS), ("nmap", C.POINTER(C.c_float) * MAX_LEVELS)]
+
+
+def build(force=False):
+    so = os.path.join(HERE, "_build", "libyouth_oracle.so")
+    src = os.path.join(HERE, "youth_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", HERE, "all"], check=True, capture_output=True)
+    return so
+
+
+_libs = {}
+
+
+def lib(fast=False):
+    key = "fast" if fast else "parity"
+    if key in _libs:
+        return _libs[key]
+    build()
+    path = os.path.join(HERE, "_build", "libyouth_oracle_fast.so" if fast else "libyouth_oracle.so")
+    L = C.CDLL(path)
+    CP = C.POINTER(OracleConfig)
+    FP = C.POINTER(Frame)
+    sig = {
+        "yo_default_config": (None, [CP]),
+        "yo_level_geometry": (C.c_int, [CP, C.c_int, C.POINTER(Level)]),
+        "yo_frame_alloc": (FP, [CP]),
+        "yo_frame_free": (None, [FP]),
+        "yo_bilateral": (None, [CP, C.c_void_p, C.c_void_p]),
+        "yo_pyrdown": (None, [CP, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+        "yo_vertex_normal": (None, [CP, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+        "yo_preprocess": (None, [CP, C.c_void_p, FP]),
+        "yo_icp_sums": (None, [CP, C.c_int, FP, FP, C.c_void_p, C.c_void_p, C.c_void_p]),
+        "yo_solve_update": (C.c_int, [CP, C.c_void_p, C.c_void_p, C.c_void_p]),
+        "yo_track_pair": (C.c_uint32, [CP, FP, FP, C.c_void_p, C.POINTER(C.c_int32)]),
+        "yo_compose": (None, [C.c_void_p, C.c_void_p, C.c_void_p]),
+        "yo_track_sequence": (C.c_double, [CP, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _libs[key] = L
+    return L
+
+
+def default_config(**overrides) -> OracleConfig:
+    cfg = OracleConfig()
+    lib().yo_default_config(C.byref(cfg))
+    for k, v in overrides.items():
+        if k == "iters":
+            for i, it in enumerate(v):
+                cfg.iters[i] = int(it)
+        else:
+            setattr(cfg, k, v)
+    return cfg
+
+
+def config_from(product_cfg) -> OracleConfig:
+    """Copy the fields the oracle shares with youth_cuda_config (same names)."""
+    cfg = OracleConfig()
+    for name, _ in OracleConfig._fields_:
+        if name == "iters":
+            for i in range(MAX_LEVELS):
+                cfg.iters[i] = product_cfg.iters[i]
+        else:
+            setattr(cfg, name, getattr(product_cfg, name))
+    return cfg
+
+
+def level_geometry(cfg, level) -> Level:
+    g = Level()
+    assert lib().yo_level_geometry(C.byref(cfg), level, C.byref(g))
+    return g
+
+
+class OFrame:
+    """One preprocessed frame held by the oracle; numpy views into its buffers."""
+
+    def __init__(self, cfg, raw=None, fast=False):
+        self.cfg = cfg
+        self.L = lib(fast)
+        self.ptr = self.L.yo_frame_alloc(C.byref(cfg))
+        if raw is not None:
+            self.preprocess(raw)
+
+    def preprocess(self, raw):
+        assert raw.dtype == np.uint16 and raw.flags.c_contiguous
+        self.L.yo_preprocess(C.byref(self.cfg), raw.ctypes.data, self.ptr)
+
+    def _view(self, field, level, ctype, comps):
+        h, w = self.cfg.height >> level, self.cfg.width >> level
+        p = getattr(self.ptr.contents, field)[level]
+        arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=(h * w * comps,))
+        return arr.reshape((h, w, comps) if comps > 1 else (h, w))
+
+    def depth(self, level):
+        return self._view("depth", level, C.c_float, 1)
+
+    def pyrcnt(self, level):
+        return self._view("pyrcnt", level, C.c_uint8, 1)
+
+    def vmap(self, level):
+        return self._view("vmap", level, C.c_float, 4)
+
+    def nmap(self, level):
+        return self._view("nmap", level, C.c_float, 4)
+
+    def mask(self, level):
+        return ((self.vmap(level)[..., 3] != 0).astype(np.uint8) | ((self.nmap(level)[..., 3] != 0).astype(np.uint8) << 1))
+
+    def __del__(self):
+        try:
+            self.L.yo_frame_free(self.ptr)
+        except Exception:
+            pass
+
+
+def icp_sums(cfg, level, cur: OFrame, prev: OFrame, pose, want_corr=True):
+    pose = np.ascontiguousarray(pose, dtype=np.float32)
+    sums = np.zeros(SUM_SLOTS, dtype=np.float64)
+    h, w = cfg.height >> level, cfg.width >> level
+    corr = np.empty((h, w), dtype=np.int32) if want_corr else None
+    lib().yo_icp_sums(C.byref(cfg), level, cur.ptr, prev.ptr, pose.ctypes.data, sums.ctypes.data,
+                      corr.ctypes.data if want_corr else None)
+    return sums, corr
+
+
+def track_pair(cfg, cur: OFrame, prev: OFrame):
+    rel = np.empty(12, dtype=np.float64)
+    inl = C.c_int32()
+    st = lib().yo_track_pair(C.byref(cfg), cur.ptr, prev.ptr, rel.ctypes.data, C.byref(inl))
+    return rel, int(st), inl.value
+
+
+def track_sequence(cfg, frames, fast=False):
+    """frames uint16 [n][H][W] -> (poses float32 [n][12], status uint32 [n], seconds)."""
+    assert frames.dtype == np.uint16 and frames.flags.c_contiguous
+    n = frames.shape[0]
+    poses = np.empty((n, 12), dtype=np.float32)
+    status = np.empty(n, dtype=np.uint32)
+    secs = lib(fast).yo_track_sequence(C.byref(cfg), frames.ctypes.data, n, poses.ctypes.data, status.ctypes.data)
+    return poses, status, secs

@@ -1,0 +1,305 @@
+"""ctypes view of include/youth_cuda.h and include/youth_host.h (no arithmetic here)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+MAX_LEVELS = 4
+SUM_SLOTS = 32
+
+MEM_HOST, MEM_DEVICE, MEM_HOST_PINNED = 0, 1, 2
+DBG_DEPTH, DBG_VERTEX, DBG_NORMAL, DBG_MASK, DBG_PYRCNT = 1, 2, 3, 4, 5
+STATUS_FIRST, STATUS_LOST = 1, 2
+
+
+class CudaLibraryMissing(RuntimeError):
+    pass
+
+
+class YouthConfig(C.Structure):
+    """Mirror of ``youth_cuda_config`` (include/youth_cuda.h)."""
+
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+        ("depth_factor", C.c_float),
+        ("levels", C.c_int32),
+        ("iters", C.c_int32 * MAX_LEVELS),
+        ("depth_min_mm", C.c_int32), ("depth_max_mm", C.c_int32),
+        ("bilateral", C.c_int32),
+        ("sigma_space_px", C.c_float), ("sigma_range_mm", C.c_float),
+        ("dist_thresh_m", C.c_float), ("cos_thresh", C.c_float),
+        ("min_inliers", C.c_int32),
+        ("icp_ppt", C.c_int32),
+        ("n_streams", C.c_int32),
+        ("batch", C.c_int32),
+        ("traj_capacity", C.c_int32),
+        ("device", C.c_int32),
+        ("stream", C.c_void_p),
+    ]
+
+
+class SynthConfig(C.Structure):
+    """Mirror of ``youth_synth_config`` (include/youth_host.h)."""
+
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+        ("seed", C.c_uint32),
+        ("period", C.c_int32),
+        ("phase", C.c_double),
+        ("dropout", C.c_double),
+        ("noise", C.c_int32),
+        ("dmin_mm", C.c_int32), ("dmax_mm", C.c_int32),
+    ]
+
+
+def lib_paths():
+    return {
+        "cuda": os.path.join(PKG_DIR, "lib", "libyouth_cuda.so"),
+        "host": os.path.join(PKG_DIR, "lib", "libAlgorithmModule.so"),
+        "harness": os.path.join(PKG_DIR, "bin", "youth_harness"),
+    }
+
+
+_cuda = None
+_host = None
+
+
+def cuda_lib():
+    """Load libyouth_cuda.so; raises loudly when the extension has not been built."""
+    global _cuda
+    if _cuda is not None:
+        return _cuda
+    path = lib_paths()["cuda"]
+    if not os.path.exists(path):
+        raise CudaLibraryMissing(
+            f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "There is no CPU fallback for the tracking path.")
+    L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    H = C.c_void_p
+    u16pp = C.POINTER(C.c_void_p)
+    sig = {
+        "youth_cuda_default_config": (C.c_int, [C.POINTER(YouthConfig)]),
+        "youth_cuda_init": (C.c_int, [C.POINTER(YouthConfig), C.POINTER(H)]),
+        "youth_cuda_destroy": (None, [H]),
+        "youth_cuda_track": (C.c_int, [H, C.c_void_p, C.c_uint32, C.c_void_p]),
+        "youth_cuda_track_batch": (C.c_int, [H, u16pp, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+        "youth_cuda_sync": (C.c_int, [H]),
+        "youth_cuda_reset": (C.c_int, [H, C.c_int]),
+        "youth_cuda_frame_count": (C.c_int, [H, C.c_int]),
+        "youth_cuda_get_trajectory": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+        "youth_cuda_last_inliers": (C.c_int, [H, C.c_int]),
+        "youth_cuda_trajectory_device_ptr": (C.c_void_p, [H, C.c_int]),
+        "youth_cuda_host_alloc": (C.c_void_p, [C.c_size_t]),
+        "youth_cuda_host_free": (None, [C.c_void_p]),
+        "youth_cuda_debug_read": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+        "youth_cuda_debug_icp": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+        "youth_cuda_timer_start": (C.c_int, [H]),
+        "youth_cuda_timer_stop": (C.c_int, [H, C.POINTER(C.c_float)]),
+        "youth_cuda_launch_count": (C.c_uint64, [H]),
+        "youth_cuda_last_error": (C.c_char_p, []),
+        "youth_cuda_abi_version": (C.c_int, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)  # AttributeError = header/library drift: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _cuda = L
+    return L
+
+
+def host_lib():
+    """Load libAlgorithmModule.so (C facade + host helpers)."""
+    global _host
+    if _host is not None:
+        return _host
+    cuda_lib()
+    path = lib_paths()["host"]
+    if not os.path.exists(path):
+        raise CudaLibraryMissing(f"{path} is missing: build the package first")
+    L = C.CDLL(path)
+    SC = C.POINTER(SynthConfig)
+    sig = {
+        "youth_synth_default": (None, [SC, C.c_int, C.c_int, C.c_int]),
+        "youth_synth_pose": (None, [SC, C.c_int, C.c_void_p]),
+        "youth_synth_gt": (None, [SC, C.c_int, C.c_void_p]),
+        "youth_synth_frame": (None, [SC, C.c_int, C.c_void_p]),
+        "youth_synth_sequence": (None, [SC, C.c_int, C.c_int, C.c_void_p]),
+        "youth_config_from_yaml": (C.c_int, [C.c_char_p, C.POINTER(YouthConfig)]),
+        "youth_pose_to_quat": (None, [C.c_void_p, C.c_void_p]),
+        "youth_tum_write": (C.c_int, [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]),
+        "youth_chunk_count": (C.c_int, [C.c_size_t]),
+        "youth_chunk_build": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_void_p,
+                                           C.c_size_t, C.c_int]),
+        "youth_reasm_create": (C.c_void_p, []),
+        "youth_reasm_destroy": (None, [C.c_void_p]),
+        "youth_reasm_feed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+        "youth_reasm_depth": (C.c_void_p, [C.c_void_p]),
+        "youth_reasm_color": (C.c_void_p, [C.c_void_p]),
+        "youth_reasm_info": (None, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                    C.POINTER(C.c_uint32)]),
+        # facade (include/SLAM.h, algorithmModule.h)
+        "initSlamModule": (None, [C.c_char_p, C.c_char_p]),
+        "stopSlamModule": (None, []),
+        "processSlamFrame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32]),
+        "saveSlamMap": (C.c_int, [C.c_char_p]),
+        "isSlamModuleRunning": (C.c_int, []),
+        "getSlamMapPoints": (C.c_int, []),
+        "resetSlam": (None, []),
+        "algorithmModule": (C.c_void_p, [C.c_void_p]),
+        "youthSlamSetOptions": (None, [C.c_int, C.c_int]),
+        "youthSlamDrain": (None, []),
+        "youthSlamGetTrajectory": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+        "youthSlamStats": (None, [C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_long)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _host = L
+    return L
+
+
+def default_config(**overrides) -> YouthConfig:
+    cfg = YouthConfig()
+    if not cuda_lib().youth_cuda_default_config(C.byref(cfg)):
+        raise RuntimeError("youth_cuda_default_config failed")
+    for k, v in overrides.items():
+        if k == "iters":
+            for i, it in enumerate(v):
+                cfg.iters[i] = int(it)
+        else:
+            setattr(cfg, k, v)
+    return cfg
+
+
+def synth_config(width=640, height=480, sequence=0, noise=0) -> SynthConfig:
+    sc = SynthConfig()
+    host_lib().youth_synth_default(C.byref(sc), width, height, sequence)
+    sc.noise = noise
+    return sc
+
+
+def synth_sequence(n, width=640, height=480, sequence=0, noise=0, first=0) -> np.ndarray:
+    """uint16 [n][height][width] synthetic depth (mm) from the C generator."""
+    sc = synth_config(width, height, sequence, noise)
+    out = np.empty((n, height, width), dtype=np.uint16)
+    host_lib().youth_synth_sequence(C.byref(sc), first, n, out.ctypes.data)
+    return out
+
+
+def synth_gt(n, width=640, height=480, sequence=0) -> np.ndarray:
+    """float64 [n][12] ground-truth camera poses relative to frame 0."""
+    sc = synth_config(width, height, sequence)
+    out = np.empty((n, 12), dtype=np.float64)
+    for i in range(n):
+        host_lib().youth_synth_gt(C.byref(sc), i, out[i].ctypes.data)
+    return out
+
+
+class Tracker:
+    """Thin object view of a ``youth_cuda_handle``."""
+
+    def __init__(self, cfg: YouthConfig):
+        self.lib = cuda_lib()
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        if not self.lib.youth_cuda_init(C.byref(cfg), C.byref(self.h)):
+            raise RuntimeError("youth_cuda_init failed: " + self.lib.youth_cuda_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.lib.youth_cuda_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, ok, what):
+        if not ok:
+            raise RuntimeError(f"{what} failed: " + self.lib.youth_cuda_last_error().decode())
+
+    def level_shape(self, level):
+        return self.cfg.height >> level, self.cfg.width >> level
+
+    def track(self, frame: np.ndarray, ts=0, want_pose=True):
+        assert frame.dtype == np.uint16 and frame.flags.c_contiguous
+        pose = np.empty(12, dtype=np.float32) if want_pose else None
+        self._check(self.lib.youth_cuda_track(self.h, frame.ctypes.data, ts, pose.ctypes.data if want_pose else None),
+                    "youth_cuda_track")
+        return pose
+
+    def track_batch_ptrs(self, ptrs, n, mem_kind, ts=None, poses_out=None):
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        self._check(self.lib.youth_cuda_track_batch(
+            self.h, arr, n, mem_kind,
+            ts.ctypes.data if ts is not None else None,
+            poses_out.ctypes.data if poses_out is not None else None), "youth_cuda_track_batch")
+
+    def track_batch(self, frames, want_poses=True):
+        """frames: list (one per stream) of uint16 [n][H][W] host arrays."""
+        n = frames[0].shape[0]
+        for f in frames:
+            assert f.dtype == np.uint16 and f.flags.c_contiguous and f.shape[0] == n
+        poses = np.empty((len(frames), n, 12), dtype=np.float32) if want_poses else None
+        self.track_batch_ptrs([f.ctypes.data for f in frames], n, MEM_HOST, None, poses)
+        return poses
+
+    def sync(self):
+        self._check(self.lib.youth_cuda_sync(self.h), "youth_cuda_sync")
+
+    def reset(self, stream=-1):
+        self._check(self.lib.youth_cuda_reset(self.h, stream), "youth_cuda_reset")
+
+    def frame_count(self, stream=0):
+        return self.lib.youth_cuda_frame_count(self.h, stream)
+
+    def trajectory(self, stream=0):
+        n = self.frame_count(stream)
+        poses = np.empty((n, 12), dtype=np.float32)
+        ts = np.empty(n, dtype=np.uint32)
+        st = np.empty(n, dtype=np.uint32)
+        got = self.lib.youth_cuda_get_trajectory(self.h, stream, 0, n, poses.ctypes.data, ts.ctypes.data, st.ctypes.data)
+        if got < 0:
+            raise RuntimeError("youth_cuda_get_trajectory failed: " + self.lib.youth_cuda_last_error().decode())
+        return poses[:got], ts[:got], st[:got]
+
+    def last_inliers(self, stream=0):
+        return self.lib.youth_cuda_last_inliers(self.h, stream)
+
+    def debug_read(self, what, frame, level, stream=0):
+        h, w = self.level_shape(level)
+        if what == DBG_DEPTH:
+            out = np.empty((h, w), dtype=np.float32)
+        elif what in (DBG_VERTEX, DBG_NORMAL):
+            out = np.empty((h, w, 4), dtype=np.float32)
+        else:
+            out = np.empty((h, w), dtype=np.uint8)
+        self._check(self.lib.youth_cuda_debug_read(self.h, what, stream, frame, level, out.ctypes.data, out.nbytes),
+                    "youth_cuda_debug_read")
+        return out
+
+    def debug_icp(self, frame, level, pose, stream=0, want_corr=True):
+        h, w = self.level_shape(level)
+        pose = np.ascontiguousarray(pose, dtype=np.float32)
+        sums = np.empty(SUM_SLOTS, dtype=np.float64)
+        corr = np.empty((h, w), dtype=np.int32) if want_corr else None
+        self._check(self.lib.youth_cuda_debug_icp(self.h, stream, frame, level, pose.ctypes.data, sums.ctypes.data,
+                                                  corr.ctypes.data if want_corr else None), "youth_cuda_debug_icp")
+        return sums, corr
+
+    def timer_start(self):
+        self._check(self.lib.youth_cuda_timer_start(self.h), "youth_cuda_timer_start")
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._check(self.lib.youth_cuda_timer_stop(self.h, C.byref(ms)), "youth_cuda_timer_stop")
+        return ms.value
+
+    def launch_count(self):
+        return int(self.lib.youth_cuda_launch_count(self.h))

@@ -1,0 +1,697 @@
+/*
+ * youth_cuda.cu -- libyouth_cuda.so: the C ABI declared in include/youth_cuda.h over the
+ * sm_100a kernels in youth_kernels.cuh.  No CPU fallback: every compute entry point
+ * fails (returns 0, youth_cuda_last_error() says why) when no CUDA device is usable.
+ *
+ * Device-resident state per handle (all in HBM, sized at init, nothing allocated per frame):
+ *   ring      per stream R = batch+1 slots; per slot and pyramid level: float depth,
+ *             float4 vertex map, float4 normal map, uint8 pyramid count
+ *   raw       2 x [S][batch] uint16 frames (double-buffered H2D landing zone)
+ *   pairs     per (stream, frame-in-group): double+float relative pose, per-tile partial
+ *             sums [max_tiles][32] float, reduced sums [32] double, status
+ *   sequence  per stream: frame count, world pose (double), trajectory [cap][12] float,
+ *             status [cap], last inlier count
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "youth_cuda.h"
+#include "youth_kernels.cuh"
+
+/* ------------------------------------------------------------------ errors */
+
+static thread_local char g_err[512] = "";
+
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 0;
+}
+
+#define CU(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e__ = (call);                                                          \
+    if (e__ != cudaSuccess) return fail("%s failed: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+extern "C" const char* youth_cuda_last_error(void) { return g_err; }
+extern "C" int youth_cuda_abi_version(void) { return YOUTH_CUDA_ABI_VERSION; }
+
+/* ------------------------------------------------------------------ handle */
+
+struct youth_cuda_handle {
+  youth_cuda_config cfg;
+  int S, B, R, P; /* streams, batch, ring slots, max pairs */
+  LevelGeom lv[YOUTH_MAX_LEVELS];
+  int npix[YOUTH_MAX_LEVELS];
+  int ntiles[YOUTH_MAX_LEVELS];
+  int max_tiles;
+  int tile_px;
+  cudaStream_t stream, copy_stream;
+  bool own_stream;
+  /* ring */
+  float* depth[YOUTH_MAX_LEVELS];
+  float4* vmap[YOUTH_MAX_LEVELS];
+  float4* nmap[YOUTH_MAX_LEVELS];
+  uint8_t* pyrcnt[YOUTH_MAX_LEVELS];
+  /* raw landing zone */
+  uint16_t* raw[2];
+  uint16_t* pinned[2];
+  cudaEvent_t raw_free[2], raw_ready[2];
+  bool raw_used[2];
+  int raw_turn;
+  /* bilateral tables */
+  float ws[49];
+  float* wr;
+  int range_cut;
+  /* pair state */
+  double* pose_d;
+  float* pose_f;
+  float* partials;
+  double* sums;
+  uint32_t* pair_status;
+  /* sequence state */
+  int* seq_count;
+  double* world;
+  float* traj;
+  uint32_t* traj_status;
+  int* last_inliers;
+  int* h_count;      /* host mirror of seq_count */
+  uint32_t* h_ts;    /* [S][cap] timestamps (host only) */
+  long long total;   /* frames per stream since init / full reset (ring position) */
+  int32_t* corr_dbg; /* debug correspondence map (level-0 sized) */
+  cudaEvent_t t0, t1;
+  uint64_t launches;
+};
+
+extern "C" int youth_cuda_default_config(youth_cuda_config* c) {
+  if (!c) return fail("null config");
+  memset(c, 0, sizeof(*c));
+  c->width = 640;
+  c->height = 480;
+  c->fx = 570.3f;
+  c->fy = 570.3f;
+  c->cx = 320.0f;
+  c->cy = 240.0f;
+  c->depth_factor = 1000.0f;
+  c->levels = 3;
+  c->iters[0] = 10;
+  c->iters[1] = 5;
+  c->iters[2] = 4;
+  c->iters[3] = 4;
+  c->depth_min_mm = 1;
+  c->depth_max_mm = 10000;
+  c->bilateral = 1;
+  c->sigma_space_px = 4.5f;
+  c->sigma_range_mm = 30.0f;
+  c->dist_thresh_m = 0.10f;
+  c->cos_thresh = 0.93969262f;
+  c->min_inliers = 100;
+  c->icp_ppt = 4;
+  c->n_streams = 1;
+  c->batch = 8;
+  c->traj_capacity = 4096;
+  c->device = 0;
+  c->stream = NULL;
+  return 1;
+}
+
+static int validate(const youth_cuda_config* c) {
+  if (c->levels < 1 || c->levels > YOUTH_MAX_LEVELS) return fail("levels must be 1..%d", YOUTH_MAX_LEVELS);
+  const int div = 1 << (c->levels - 1);
+  if (c->width <= 0 || c->height <= 0 || c->width % 8 || c->width % div || c->height % div)
+    return fail("width/height must be positive, width %% 8 == 0, both divisible by 2^(levels-1)");
+  if (c->width > 16384 || c->height > 16384) return fail("image too large");
+  if (!(c->fx > 0.f) || !(c->fy > 0.f) || !(c->depth_factor > 0.f)) return fail("bad intrinsics / depth factor");
+  if (c->depth_min_mm < 1 || c->depth_max_mm > 65535 || c->depth_min_mm > c->depth_max_mm)
+    return fail("depth range must satisfy 1 <= min <= max <= 65535");
+  if (c->icp_ppt != 1 && c->icp_ppt != 2 && c->icp_ppt != 4 && c->icp_ppt != 8) return fail("icp_ppt must be 1, 2, 4 or 8");
+  if (c->n_streams < 1 || c->n_streams > YK_MAX_STREAMS) return fail("n_streams must be 1..%d", YK_MAX_STREAMS);
+  if (c->batch < 1 || c->batch > 1024) return fail("batch must be 1..1024");
+  if (c->traj_capacity < 1) return fail("traj_capacity must be >= 1");
+  if (c->bilateral && !(c->sigma_space_px > 0.f && c->sigma_range_mm > 0.f)) return fail("bilateral sigmas must be > 0");
+  for (int l = 0; l < c->levels; ++l)
+    if (c->iters[l] < 0 || c->iters[l] > 1000) return fail("iters[%d] out of range", l);
+  return 1;
+}
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t count) {
+  cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+  if (e == cudaSuccess) e = cudaMemset(*p, 0, count * sizeof(T));
+  return e;
+}
+
+extern "C" void youth_cuda_destroy(youth_cuda_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  for (int l = 0; l < YOUTH_MAX_LEVELS; ++l) {
+    cudaFree(h->depth[l]);
+    cudaFree(h->vmap[l]);
+    cudaFree(h->nmap[l]);
+    cudaFree(h->pyrcnt[l]);
+  }
+  for (int k = 0; k < 2; ++k) {
+    cudaFree(h->raw[k]);
+    if (h->pinned[k]) cudaFreeHost(h->pinned[k]);
+    if (h->raw_free[k]) cudaEventDestroy(h->raw_free[k]);
+    if (h->raw_ready[k]) cudaEventDestroy(h->raw_ready[k]);
+  }
+  cudaFree(h->wr);
+  cudaFree(h->pose_d);
+  cudaFree(h->pose_f);
+  cudaFree(h->partials);
+  cudaFree(h->sums);
+  cudaFree(h->pair_status);
+  cudaFree(h->seq_count);
+  cudaFree(h->world);
+  cudaFree(h->traj);
+  cudaFree(h->traj_status);
+  cudaFree(h->last_inliers);
+  cudaFree(h->corr_dbg);
+  if (h->t0) cudaEventDestroy(h->t0);
+  if (h->t1) cudaEventDestroy(h->t1);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  free(h->h_count);
+  free(h->h_ts);
+  delete h;
+}
+
+static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail("no CUDA device available (%s); libyouth_cuda has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail("device %d out of range (have %d)", cfg->device, ndev);
+  CU(cudaSetDevice(cfg->device));
+  h->cfg = *cfg;
+  h->S = cfg->n_streams;
+  h->B = cfg->batch;
+  h->R = cfg->batch + 1;
+  h->P = h->S * h->B;
+  /* per-level geometry: identical float operation sequence to the checker */
+  {
+    int w = cfg->width, hh = cfg->height;
+    float fx = cfg->fx, fy = cfg->fy, cx = cfg->cx, cy = cfg->cy;
+    for (int l = 0; l < cfg->levels; ++l) {
+      if (l > 0) {
+        w /= 2;
+        hh /= 2;
+        fx = fx * 0.5f;
+        fy = fy * 0.5f;
+        cx = (cx - 0.5f) * 0.5f;
+        cy = (cy - 0.5f) * 0.5f;
+      }
+      h->lv[l] = LevelGeom{w, hh, fx, fy, cx, cy};
+      h->npix[l] = w * hh;
+    }
+  }
+  h->tile_px = YOUTH_ICP_THREADS * cfg->icp_ppt;
+  h->max_tiles = 0;
+  for (int l = 0; l < cfg->levels; ++l) {
+    h->ntiles[l] = (h->npix[l] + h->tile_px - 1) / h->tile_px;
+    if (h->ntiles[l] > h->max_tiles) h->max_tiles = h->ntiles[l];
+  }
+  if (cfg->stream) {
+    h->stream = (cudaStream_t)cfg->stream;
+    h->own_stream = false;
+  } else {
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+  }
+  CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  const size_t slots = (size_t)h->S * h->R;
+  for (int l = 0; l < cfg->levels; ++l) {
+    CU(dalloc(&h->depth[l], slots * h->npix[l]));
+    CU(dalloc(&h->vmap[l], slots * h->npix[l]));
+    CU(dalloc(&h->nmap[l], slots * h->npix[l]));
+    CU(dalloc(&h->pyrcnt[l], slots * h->npix[l]));
+  }
+  const size_t frame_px = (size_t)cfg->width * cfg->height;
+  for (int k = 0; k < 2; ++k) {
+    CU(dalloc(&h->raw[k], (size_t)h->P * frame_px));
+    CU(cudaHostAlloc((void**)&h->pinned[k], (size_t)h->P * frame_px * sizeof(uint16_t), cudaHostAllocDefault));
+    CU(cudaEventCreateWithFlags(&h->raw_free[k], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->raw_ready[k], cudaEventDisableTiming));
+  }
+  /* bilateral tables (the only libm use; depends on the config alone) */
+  {
+    int cut = (int)(3.0f * cfg->sigma_range_mm);
+    if (cut > YK_RANGE_LUT_MAX - 2) cut = YK_RANGE_LUT_MAX - 2;
+    if (cut < 0) cut = 0;
+    h->range_cut = cut;
+    const double ss = (double)cfg->sigma_space_px, sr = (double)cfg->sigma_range_mm;
+    for (int dy = -3; dy <= 3; ++dy)
+      for (int dx = -3; dx <= 3; ++dx)
+        h->ws[(dy + 3) * 7 + dx + 3] = cfg->bilateral ? (float)exp(-(double)(dx * dx + dy * dy) / (2.0 * ss * ss)) : 0.f;
+    float wr[YK_RANGE_LUT_MAX];
+    for (int i = 0; i <= cut; ++i) wr[i] = cfg->bilateral ? (float)exp(-((double)i * (double)i) / (2.0 * sr * sr)) : 0.f;
+    wr[cut + 1] = 0.0f;
+    CU(dalloc(&h->wr, (size_t)YK_RANGE_LUT_MAX));
+    CU(cudaMemcpy(h->wr, wr, sizeof(float) * (cut + 2), cudaMemcpyHostToDevice));
+  }
+  CU(dalloc(&h->pose_d, (size_t)h->P * 12));
+  CU(dalloc(&h->pose_f, (size_t)h->P * 12));
+  CU(dalloc(&h->partials, (size_t)h->P * h->max_tiles * 32));
+  CU(dalloc(&h->sums, (size_t)h->P * 32));
+  CU(dalloc(&h->pair_status, (size_t)h->P));
+  CU(dalloc(&h->seq_count, (size_t)h->S));
+  CU(dalloc(&h->world, (size_t)h->S * 12));
+  CU(dalloc(&h->traj, (size_t)h->S * cfg->traj_capacity * 12));
+  CU(dalloc(&h->traj_status, (size_t)h->S * cfg->traj_capacity));
+  CU(dalloc(&h->last_inliers, (size_t)h->S));
+  CU(dalloc(&h->corr_dbg, frame_px));
+  h->h_count = (int*)calloc(h->S, sizeof(int));
+  h->h_ts = (uint32_t*)calloc((size_t)h->S * cfg->traj_capacity, sizeof(uint32_t));
+  if (!h->h_count || !h->h_ts) return fail("host allocation failed");
+  CU(cudaEventCreate(&h->t0));
+  CU(cudaEventCreate(&h->t1));
+  CU(cudaDeviceSynchronize());
+  return 1;
+}
+
+extern "C" int youth_cuda_init(const youth_cuda_config* cfg, youth_cuda_handle** out) {
+  if (!cfg || !out) return fail("null argument");
+  *out = NULL;
+  if (!validate(cfg)) return 0;
+  youth_cuda_handle* h = new youth_cuda_handle();
+  memset((void*)h, 0, sizeof(*h));
+  if (!init_impl(cfg, h)) {
+    char keep[sizeof(g_err)];
+    memcpy(keep, g_err, sizeof(keep));
+    youth_cuda_destroy(h);
+    memcpy(g_err, keep, sizeof(keep));
+    return 0;
+  }
+  *out = h;
+  return 1;
+}
+
+/* ------------------------------------------------------------------ launches */
+
+static RingGeom ring_of(const youth_cuda_handle* h, int n) {
+  RingGeom r;
+  r.n = n;
+  r.head = (int)(h->total % h->R);
+  r.R = h->R;
+  r.S = h->S;
+  return r;
+}
+
+template <bool DEBUG>
+static void launch_icp(youth_cuda_handle* h, const IcpParams& ip, dim3 grid) {
+  switch (h->cfg.icp_ppt) {
+    case 1: k_icp<1, DEBUG><<<grid, YOUTH_ICP_THREADS, 0, h->stream>>>(ip); break;
+    case 2: k_icp<2, DEBUG><<<grid, YOUTH_ICP_THREADS, 0, h->stream>>>(ip); break;
+    case 4: k_icp<4, DEBUG><<<grid, YOUTH_ICP_THREADS, 0, h->stream>>>(ip); break;
+    default: k_icp<8, DEBUG><<<grid, YOUTH_ICP_THREADS, 0, h->stream>>>(ip); break;
+  }
+  h->launches++;
+}
+
+static IcpParams icp_params(const youth_cuda_handle* h, int level, const RingGeom& ring) {
+  IcpParams ip;
+  memset(&ip, 0, sizeof(ip));
+  ip.vmap = h->vmap[level];
+  ip.nmap = h->nmap[level];
+  ip.g = h->lv[level];
+  ip.ring = ring;
+  ip.npix = h->npix[level];
+  ip.ntiles = h->ntiles[level];
+  ip.max_tiles = h->max_tiles;
+  ip.dist2_thr = h->cfg.dist_thresh_m * h->cfg.dist_thresh_m;
+  ip.cos_thr = h->cfg.cos_thresh;
+  ip.pose_f = h->pose_f;
+  ip.seq_count = h->seq_count;
+  ip.partials = h->partials;
+  ip.corr = NULL;
+  ip.dbg_cur_slot = -1;
+  ip.dbg_prev_slot = -1;
+  ip.dbg_stream = 0;
+  return ip;
+}
+
+/* enqueue the whole schedule for n frames of every stream; raw_dev[s] = device pointers */
+static int enqueue_group(youth_cuda_handle* h, const uint16_t* const* raw_dev, int n) {
+  const youth_cuda_config& c = h->cfg;
+  const RingGeom ring = ring_of(h, n);
+  const int frames = h->S * n;
+  /* stage 1 + 2a */
+  {
+    IngestParams ip;
+    memset(&ip, 0, sizeof(ip));
+    for (int s = 0; s < h->S; ++s) ip.raw[s] = raw_dev[s];
+    for (int l = 0; l < c.levels; ++l) {
+      ip.depth[l] = h->depth[l];
+      ip.vmap[l] = h->vmap[l];
+      ip.pyrcnt[l] = h->pyrcnt[l];
+      ip.lv[l] = h->lv[l];
+    }
+    ip.ring = ring;
+    ip.levels = c.levels;
+    ip.dmin = c.depth_min_mm;
+    ip.dmax = c.depth_max_mm;
+    ip.range_cut = h->range_cut;
+    memcpy(ip.ws, h->ws, sizeof(ip.ws));
+    ip.wr = h->wr;
+    ip.depth_factor = c.depth_factor;
+    ip.pyr_thr = 3.0f * c.sigma_range_mm;
+    dim3 grid((c.width + YK_TILE_W - 1) / YK_TILE_W, (c.height + YK_TILE_H - 1) / YK_TILE_H, frames);
+    if (c.bilateral)
+      k_ingest<true><<<grid, 256, 0, h->stream>>>(ip);
+    else
+      k_ingest<false><<<grid, 256, 0, h->stream>>>(ip);
+    h->launches++;
+  }
+  /* stage 2b */
+  {
+    NormalParams np;
+    memset(&np, 0, sizeof(np));
+    int total = 0;
+    for (int l = 0; l < c.levels; ++l) {
+      np.vmap[l] = h->vmap[l];
+      np.nmap[l] = h->nmap[l];
+      np.lv[l] = h->lv[l];
+      total += h->npix[l];
+    }
+    np.ring = ring;
+    np.levels = c.levels;
+    dim3 grid((total + 255) / 256, frames);
+    k_normals<<<grid, 256, 0, h->stream>>>(np);
+    h->launches++;
+  }
+  /* stages 3-5: coarse to fine, fixed iteration schedule, no host sync */
+  k_init_pairs<<<(frames + 127) / 128, 128, 0, h->stream>>>(frames, h->pose_d, h->pose_f, h->pair_status);
+  h->launches++;
+  SolveParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.partials = h->partials;
+  sp.max_tiles = h->max_tiles;
+  sp.ring = ring;
+  sp.seq_count = h->seq_count;
+  sp.pose_d = h->pose_d;
+  sp.pose_f = h->pose_f;
+  sp.sums = h->sums;
+  sp.pair_status = h->pair_status;
+  sp.min_inliers = c.min_inliers;
+  sp.do_solve = 1;
+  for (int level = c.levels - 1; level >= 0; --level) {
+    const IcpParams ip = icp_params(h, level, ring);
+    sp.ntiles = h->ntiles[level];
+    for (int it = 0; it < c.iters[level]; ++it) {
+      launch_icp<false>(h, ip, dim3(h->ntiles[level], frames));
+      k_solve<<<frames, 256, 0, h->stream>>>(sp);
+      h->launches++;
+    }
+  }
+  /* pose chain + trajectory append */
+  {
+    ComposeParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.ring = ring;
+    cp.seq_count = h->seq_count;
+    cp.world = h->world;
+    cp.pose_d = h->pose_d;
+    cp.sums = h->sums;
+    cp.pair_status = h->pair_status;
+    cp.traj = h->traj;
+    cp.traj_status = h->traj_status;
+    cp.last_inliers = h->last_inliers;
+    cp.cap = c.traj_capacity;
+    k_compose<<<(h->S + 63) / 64, 64, 0, h->stream>>>(cp);
+    h->launches++;
+  }
+  CU(cudaGetLastError());
+  return 1;
+}
+
+extern "C" int youth_cuda_track_batch(youth_cuda_handle* h, const uint16_t* const* depth, int n_frames,
+                                      int mem_kind, const uint32_t* timestamps_ms, float* poses_out) {
+  if (!h || !depth) return fail("null argument");
+  if (n_frames < 1 || n_frames > h->B) return fail("n_frames must be 1..batch (%d)", h->B);
+  for (int s = 0; s < h->S; ++s) {
+    if (!depth[s]) return fail("depth[%d] is NULL", s);
+    if (h->h_count[s] + n_frames > h->cfg.traj_capacity) return fail("trajectory capacity (%d) exceeded", h->cfg.traj_capacity);
+  }
+  CU(cudaSetDevice(h->cfg.device));
+  const size_t frame_px = (size_t)h->cfg.width * h->cfg.height;
+  const size_t seq_bytes = frame_px * sizeof(uint16_t) * (size_t)n_frames;
+  const uint16_t* dev_ptrs[YK_MAX_STREAMS];
+  if (mem_kind == YOUTH_MEM_DEVICE) {
+    for (int s = 0; s < h->S; ++s) dev_ptrs[s] = depth[s];
+    if (!enqueue_group(h, dev_ptrs, n_frames)) return 0;
+  } else if (mem_kind == YOUTH_MEM_HOST || mem_kind == YOUTH_MEM_HOST_PINNED) {
+    const int k = h->raw_turn;
+    h->raw_turn ^= 1;
+    /* the landing zone may still be read by the group launched two calls ago */
+    if (h->raw_used[k]) {
+      if (mem_kind == YOUTH_MEM_HOST)
+        CU(cudaEventSynchronize(h->raw_free[k])); /* the pinned staging copy is about to be overwritten */
+      CU(cudaStreamWaitEvent(h->copy_stream, h->raw_free[k], 0));
+    }
+    for (int s = 0; s < h->S; ++s) {
+      uint16_t* dst = h->raw[k] + (size_t)s * n_frames * frame_px;
+      const uint16_t* src = depth[s];
+      if (mem_kind == YOUTH_MEM_HOST) {
+        uint16_t* stage = h->pinned[k] + (size_t)s * n_frames * frame_px;
+        memcpy(stage, src, seq_bytes); /* synchronous copy: the caller may reuse its buffer (SLAM.cpp:133-134) */
+        src = stage;
+      }
+      CU(cudaMemcpyAsync(dst, src, seq_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+      dev_ptrs[s] = dst;
+    }
+    CU(cudaEventRecord(h->raw_ready[k], h->copy_stream));
+    CU(cudaStreamWaitEvent(h->stream, h->raw_ready[k], 0));
+    if (!enqueue_group(h, dev_ptrs, n_frames)) return 0;
+    CU(cudaEventRecord(h->raw_free[k], h->stream));
+    h->raw_used[k] = true;
+  } else {
+    return fail("unknown mem_kind %d", mem_kind);
+  }
+  for (int s = 0; s < h->S; ++s) {
+    for (int i = 0; i < n_frames; ++i)
+      h->h_ts[(size_t)s * h->cfg.traj_capacity + h->h_count[s] + i] =
+          timestamps_ms ? timestamps_ms[i] : (uint32_t)(((long long)(h->h_count[s] + i) * 100) / 3);
+    h->h_count[s] += n_frames;
+  }
+  h->total += n_frames;
+  if (poses_out) {
+    for (int s = 0; s < h->S; ++s) {
+      const float* src = h->traj + ((size_t)s * h->cfg.traj_capacity + (h->h_count[s] - n_frames)) * 12;
+      CU(cudaMemcpyAsync(poses_out + (size_t)s * n_frames * 12, src, sizeof(float) * 12 * n_frames,
+                         cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  return 1;
+}
+
+extern "C" int youth_cuda_track(youth_cuda_handle* h, const uint16_t* depth_mm, uint32_t timestamp_ms,
+                                float pose_out[12]) {
+  if (!h) return fail("null handle");
+  if (h->S != 1) return fail("youth_cuda_track needs a single-sequence handle (n_streams == 1)");
+  const uint16_t* d[1] = {depth_mm};
+  return youth_cuda_track_batch(h, d, 1, YOUTH_MEM_HOST, &timestamp_ms, pose_out);
+}
+
+extern "C" int youth_cuda_sync(youth_cuda_handle* h) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->copy_stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 1;
+}
+
+extern "C" int youth_cuda_reset(youth_cuda_handle* h, int stream) {
+  if (!h) return fail("null handle");
+  if (stream < -1 || stream >= h->S) return fail("stream out of range");
+  CU(cudaSetDevice(h->cfg.device));
+  if (stream < 0) {
+    CU(cudaMemsetAsync(h->seq_count, 0, sizeof(int) * h->S, h->stream));
+    CU(cudaMemsetAsync(h->last_inliers, 0, sizeof(int) * h->S, h->stream));
+    memset(h->h_count, 0, sizeof(int) * h->S);
+    CU(cudaStreamSynchronize(h->stream));
+    h->total = 0;
+  } else {
+    CU(cudaMemsetAsync(h->seq_count + stream, 0, sizeof(int), h->stream));
+    CU(cudaMemsetAsync(h->last_inliers + stream, 0, sizeof(int), h->stream));
+    h->h_count[stream] = 0;
+  }
+  return 1;
+}
+
+extern "C" int youth_cuda_frame_count(youth_cuda_handle* h, int stream) {
+  if (!h || stream < 0 || stream >= h->S) return -1;
+  return h->h_count[stream];
+}
+
+extern "C" int youth_cuda_get_trajectory(youth_cuda_handle* h, int stream, int first, int max_frames,
+                                         float* poses_out, uint32_t* timestamps_out, uint32_t* status_out) {
+  if (!h || stream < 0 || stream >= h->S || first < 0 || max_frames < 0) {
+    fail("bad argument");
+    return -1;
+  }
+  int n = h->h_count[stream] - first;
+  if (n > max_frames) n = max_frames;
+  if (n <= 0) return 0;
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return -1;
+  const size_t base = (size_t)stream * h->cfg.traj_capacity + first;
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess && poses_out)
+    e = cudaMemcpy(poses_out, h->traj + base * 12, sizeof(float) * 12 * n, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && status_out)
+    e = cudaMemcpy(status_out, h->traj_status + base, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) {
+    fail("trajectory read-back failed: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  if (timestamps_out) memcpy(timestamps_out, h->h_ts + base, sizeof(uint32_t) * n);
+  return n;
+}
+
+extern "C" int youth_cuda_last_inliers(youth_cuda_handle* h, int stream) {
+  if (!h || stream < 0 || stream >= h->S) return -1;
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return -1;
+  int v = 0;
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+  if (cudaMemcpy(&v, h->last_inliers + stream, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return v;
+}
+
+extern "C" void* youth_cuda_trajectory_device_ptr(youth_cuda_handle* h, int stream) {
+  if (!h || stream < 0 || stream >= h->S) return NULL;
+  return h->traj + (size_t)stream * h->cfg.traj_capacity * 12;
+}
+
+extern "C" void* youth_cuda_host_alloc(size_t bytes) {
+  void* p = NULL;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    fail("cudaHostAlloc(%zu) failed", bytes);
+    return NULL;
+  }
+  return p;
+}
+
+extern "C" void youth_cuda_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+/* ------------------------------------------------------------------ parity hooks */
+
+static int slot_of_frame(const youth_cuda_handle* h, int frame) {
+  if (frame < 0 || frame >= h->total || frame < h->total - h->R) return -1;
+  return (int)(frame % h->R);
+}
+
+extern "C" int youth_cuda_debug_read(youth_cuda_handle* h, int what, int stream, int frame, int level, void* dst,
+                                     size_t dst_bytes) {
+  if (!h || !dst) return fail("null argument");
+  if (stream < 0 || stream >= h->S || level < 0 || level >= h->cfg.levels) return fail("stream/level out of range");
+  const int slot = slot_of_frame(h, frame);
+  if (slot < 0) return fail("frame %d is not resident in the ring", frame);
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  const size_t np = (size_t)h->npix[level];
+  const size_t off = ((size_t)stream * h->R + slot) * np;
+  switch (what) {
+    case YOUTH_DBG_DEPTH:
+      if (dst_bytes < np * 4) return fail("dst too small");
+      CU(cudaMemcpy(dst, h->depth[level] + off, np * 4, cudaMemcpyDeviceToHost));
+      return 1;
+    case YOUTH_DBG_VERTEX:
+    case YOUTH_DBG_NORMAL:
+      if (dst_bytes < np * 16) return fail("dst too small");
+      CU(cudaMemcpy(dst, (what == YOUTH_DBG_VERTEX ? h->vmap[level] : h->nmap[level]) + off, np * 16,
+                    cudaMemcpyDeviceToHost));
+      return 1;
+    case YOUTH_DBG_PYRCNT:
+      if (dst_bytes < np) return fail("dst too small");
+      CU(cudaMemcpy(dst, h->pyrcnt[level] + off, np, cudaMemcpyDeviceToHost));
+      return 1;
+    case YOUTH_DBG_MASK: {
+      if (dst_bytes < np) return fail("dst too small");
+      float4* tmp = (float4*)malloc(np * 16 * 2);
+      if (!tmp) return fail("host allocation failed");
+      cudaError_t e = cudaMemcpy(tmp, h->vmap[level] + off, np * 16, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMemcpy(tmp + np, h->nmap[level] + off, np * 16, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) {
+        free(tmp);
+        return fail("mask read-back failed: %s", cudaGetErrorString(e));
+      }
+      uint8_t* m = (uint8_t*)dst;
+      for (size_t i = 0; i < np; ++i) m[i] = (uint8_t)((tmp[i].w != 0.f ? 1 : 0) | (tmp[np + i].w != 0.f ? 2 : 0));
+      free(tmp);
+      return 1;
+    }
+    default:
+      return fail("unknown debug selector %d", what);
+  }
+}
+
+extern "C" int youth_cuda_debug_icp(youth_cuda_handle* h, int stream, int frame, int level, const float pose[12],
+                                    double* sums_out, int32_t* corr_out) {
+  if (!h || !pose || !sums_out) return fail("null argument");
+  if (stream < 0 || stream >= h->S || level < 0 || level >= h->cfg.levels) return fail("stream/level out of range");
+  const int cur = slot_of_frame(h, frame), prev = slot_of_frame(h, frame - 1);
+  if (cur < 0 || prev < 0) return fail("frames %d and %d must both be resident in the ring", frame - 1, frame);
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  /* pair slot 0 is free between groups: borrow it */
+  CU(cudaMemcpyAsync(h->pose_f, pose, sizeof(float) * 12, cudaMemcpyHostToDevice, h->stream));
+  RingGeom ring = ring_of(h, 1);
+  IcpParams ip = icp_params(h, level, ring);
+  ip.corr = corr_out ? h->corr_dbg : NULL;
+  ip.dbg_cur_slot = cur;
+  ip.dbg_prev_slot = prev;
+  ip.dbg_stream = stream;
+  launch_icp<true>(h, ip, dim3(h->ntiles[level], 1));
+  SolveParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.partials = h->partials;
+  sp.ntiles = h->ntiles[level];
+  sp.max_tiles = h->max_tiles;
+  sp.ring = ring;
+  sp.seq_count = h->seq_count;
+  sp.pose_d = h->pose_d;
+  sp.pose_f = h->pose_f;
+  sp.sums = h->sums;
+  sp.pair_status = h->pair_status;
+  sp.min_inliers = h->cfg.min_inliers;
+  sp.do_solve = 0;
+  k_solve<<<1, 256, 0, h->stream>>>(sp);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(sums_out, h->sums, sizeof(double) * 32, cudaMemcpyDeviceToHost, h->stream));
+  if (corr_out)
+    CU(cudaMemcpyAsync(corr_out, h->corr_dbg, sizeof(int32_t) * h->npix[level], cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 1;
+}
+
+extern "C" int youth_cuda_timer_start(youth_cuda_handle* h) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaEventRecord(h->t0, h->stream));
+  return 1;
+}
+
+extern "C" int youth_cuda_timer_stop(youth_cuda_handle* h, float* ms_out) {
+  if (!h || !ms_out) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaEventRecord(h->t1, h->stream));
+  CU(cudaEventSynchronize(h->t1));
+  CU(cudaEventElapsedTime(ms_out, h->t0, h->t1));
+  return 1;
+}
+
+extern "C" uint64_t youth_cuda_launch_count(youth_cuda_handle* h) { return h ? h->launches : 0; }

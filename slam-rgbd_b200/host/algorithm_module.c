@@ -1,0 +1,53 @@
+/*
+ * algorithm_module.c -- pthread entry of the Algorithm stage.
+ *
+ * The reference body is a call to an undeclared SLAM() (Youth.Source/AlgorithmModule/
+ * algorithmModule.c:3-5) and its launch site is commented out (main.c:279-281).  Here the
+ * thread initialises the tracker and then either serves processSlamFrame() callers (the
+ * Logging hook at loggingModule.c:354) until stopSlamModule(), or -- when `id` is a path --
+ * replays a .bin recording headless, the way playbackThread does for the viewer
+ * (loggingModule.c:542-594) but without the 30 fps pacing sleep.
+ */
+#define _GNU_SOURCE
+#include <stdio.h>
+#include <stdlib.h>
+#include <unistd.h>
+
+#include "algorithmModule.h"
+#include "youth_host.h"
+
+void youthSlamSetOptions(int lossless, int batch);
+void youthSlamDrain(void);
+
+void* algorithmModule(void* id) {
+  const char* replay = (const char*)id;
+  if (replay) youthSlamSetOptions(1, -1); /* a recording is replayed losslessly */
+  initSlamModule(getenv("YOUTH_SLAM_CONFIG"), getenv("YOUTH_SLAM_VOCAB"));
+  if (!isSlamModuleRunning()) return NULL;
+  if (!replay) {
+    while (isSlamModuleRunning()) usleep(10000);
+    return NULL;
+  }
+  FILE* f = fopen(replay, "rb");
+  if (!f) {
+    fprintf(stderr, "algorithmModule: cannot open '%s'\n", replay);
+    stopSlamModule();
+    return NULL;
+  }
+  const size_t cap = 64u << 20; /* large enough for 1280x960 and beyond (reference caps at 1 MiB) */
+  uint16_t* depth = (uint16_t*)malloc(cap);
+  FrameHeader hdr;
+  long frames = 0;
+  while (depth && youth_bin_read_frame(f, &hdr, depth, cap, NULL, 0)) {
+    if (!processSlamFrame((const int16_t*)depth, NULL, hdr.width, hdr.height, hdr.timestamp)) break;
+    ++frames;
+  }
+  fclose(f);
+  free(depth);
+  youthSlamDrain();
+  const char* out = getenv("YOUTH_SLAM_OUT");
+  if (out) saveSlamMap(out);
+  fprintf(stderr, "algorithmModule: replayed %ld frames from %s\n", frames, replay);
+  stopSlamModule();
+  return NULL;
+}

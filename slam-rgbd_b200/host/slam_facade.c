@@ -1,0 +1,283 @@
+/*
+ * slam_facade.c -- the AlgorithmModule C facade (include/SLAM.h) over libyouth_cuda.so.
+ *
+ * Replaces reference Youth.Source/AlgorithmModule/SLAM.cpp:15-228 (process-global
+ * singleton, bounded frame queue, worker thread) with:
+ *   - a page-locked host frame ring that processSlamFrame() copies into synchronously
+ *     (ownership rule of SLAM.cpp:133-134: the caller may reuse its buffer on return);
+ *   - a worker thread that hands runs of consecutive ring slots to
+ *     youth_cuda_track_batch(), i.e. the device-resident frame ring is fed straight
+ *     from the host ring with one async H2D per run;
+ *   - the reference's lossy back-pressure (more than 10 queued -> drop oldest down to 5,
+ *     SLAM.cpp:163-167) as the default, and a lossless mode (producer blocks) for
+ *     replay / benchmarking, where dropping frames would make parity meaningless.
+ * Shared flags are C11 atomics (the reference's plain bools at SLAM.cpp:17,29 are racy).
+ * No C++ exceptions exist here; errors are reported by return value and on stderr.
+ */
+#define _GNU_SOURCE
+#include <pthread.h>
+#include <stdatomic.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "SLAM.h"
+#include "youth_host.h"
+
+#define QUEUE_HIGH_WATER 10 /* SLAM.cpp:163 */
+#define QUEUE_LOW_WATER 5   /* SLAM.cpp:165 */
+
+static struct {
+  pthread_mutex_t mu;
+  pthread_cond_t nonempty, nonfull, idle;
+  atomic_int running;
+  atomic_int stop_req;
+  youth_cuda_handle* h;
+  youth_cuda_config cfg;
+  uint16_t* ring; /* pinned, qcap frames */
+  uint32_t* ts;
+  int qcap, head, count, busy; /* count = frames waiting; busy = claimed by the worker, slots still in use */
+  int lossless, batch;
+  pthread_t worker;
+  long accepted, dropped, tracked;
+  atomic_int last_inliers;
+} G = {.mu = PTHREAD_MUTEX_INITIALIZER,
+       .nonempty = PTHREAD_COND_INITIALIZER,
+       .nonfull = PTHREAD_COND_INITIALIZER,
+       .idle = PTHREAD_COND_INITIALIZER,
+       .lossless = -1,
+       .batch = -1};
+
+static size_t frame_px(void) { return (size_t)G.cfg.width * (size_t)G.cfg.height; }
+
+static void* worker_main(void* arg) {
+  (void)arg;
+  float* poses = (float*)malloc(sizeof(float) * 12 * (size_t)G.batch);
+  pthread_mutex_lock(&G.mu);
+  for (;;) {
+    while (G.count == 0 && !atomic_load(&G.stop_req)) pthread_cond_wait(&G.nonempty, &G.mu);
+    if (G.count == 0 && atomic_load(&G.stop_req)) break;
+    /* claim the longest run of consecutive slots: contiguous in the pinned ring, at most
+     * one batch.  Claimed frames leave the queue at once; `busy` fences their slots. */
+    int n = G.count;
+    if (n > G.batch) n = G.batch;
+    if (n > G.qcap - G.head) n = G.qcap - G.head;
+    const int first = G.head;
+    G.head = (G.head + n) % G.qcap;
+    G.count -= n;
+    G.busy = n;
+    pthread_mutex_unlock(&G.mu);
+
+    const uint16_t* src[1] = {G.ring + frame_px() * (size_t)first};
+    const int ok = youth_cuda_track_batch(G.h, src, n, YOUTH_MEM_HOST_PINNED, G.ts + first, poses);
+    if (!ok) fprintf(stderr, "AlgorithmModule: tracking failed: %s\n", youth_cuda_last_error());
+    else atomic_store(&G.last_inliers, youth_cuda_last_inliers(G.h, 0));
+
+    pthread_mutex_lock(&G.mu);
+    G.busy = 0;
+    G.tracked += ok ? n : 0;
+    pthread_cond_broadcast(&G.nonfull);
+    if (G.count == 0) pthread_cond_broadcast(&G.idle);
+  }
+  pthread_mutex_unlock(&G.mu);
+  free(poses);
+  return NULL;
+}
+
+void initSlamModule(const char* config_file, const char* vocabulary_file) {
+  (void)vocabulary_file; /* an ORB vocabulary has no meaning for a dense depth tracker */
+  if (atomic_load(&G.running)) {
+    fprintf(stderr, "AlgorithmModule: already running\n");
+    return;
+  }
+  if (!youth_config_from_yaml(config_file, &G.cfg)) {
+    fprintf(stderr, "AlgorithmModule: cannot read config '%s'\n", config_file ? config_file : "");
+    return;
+  }
+  if (G.lossless < 0) {
+    const char* e = getenv("YOUTH_SLAM_LOSSLESS");
+    G.lossless = (e && *e == '1') ? 1 : 0;
+  }
+  if (G.batch < 0) {
+    const char* e = getenv("YOUTH_SLAM_BATCH");
+    G.batch = e ? atoi(e) : 8;
+    if (G.batch < 1) G.batch = 1;
+    if (G.batch > 64) G.batch = 64;
+  }
+  const char* dev = getenv("YOUTH_SLAM_DEVICE");
+  G.cfg.device = dev ? atoi(dev) : 0;
+  G.cfg.n_streams = 1;
+  G.cfg.batch = G.batch;
+  const char* cap = getenv("YOUTH_SLAM_TRAJ_CAPACITY");
+  G.cfg.traj_capacity = cap ? atoi(cap) : 65536;
+  if (!youth_cuda_init(&G.cfg, &G.h)) {
+    fprintf(stderr, "AlgorithmModule: failed to initialise the CUDA tracker: %s\n", youth_cuda_last_error());
+    G.h = NULL;
+    return;
+  }
+  G.qcap = QUEUE_HIGH_WATER + 2 + 2 * G.batch; /* queue + one claimed run always fit */
+  G.ring = (uint16_t*)youth_cuda_host_alloc(frame_px() * sizeof(uint16_t) * (size_t)G.qcap);
+  G.ts = (uint32_t*)calloc((size_t)G.qcap, sizeof(uint32_t));
+  if (!G.ring || !G.ts) {
+    fprintf(stderr, "AlgorithmModule: cannot allocate the host frame ring\n");
+    youth_cuda_host_free(G.ring);
+    free(G.ts);
+    youth_cuda_destroy(G.h);
+    G.h = NULL;
+    G.ring = NULL;
+    G.ts = NULL;
+    return;
+  }
+  G.head = G.count = G.busy = 0;
+  G.accepted = G.dropped = G.tracked = 0;
+  atomic_store(&G.last_inliers, 0);
+  atomic_store(&G.stop_req, 0);
+  if (pthread_create(&G.worker, NULL, worker_main, NULL) != 0) {
+    fprintf(stderr, "AlgorithmModule: cannot start the worker thread\n");
+    youth_cuda_host_free(G.ring);
+    free(G.ts);
+    youth_cuda_destroy(G.h);
+    G.h = NULL;
+    return;
+  }
+  atomic_store(&G.running, 1);
+}
+
+void stopSlamModule(void) {
+  if (!atomic_load(&G.running)) return;
+  pthread_mutex_lock(&G.mu);
+  atomic_store(&G.stop_req, 1);
+  pthread_cond_broadcast(&G.nonempty);
+  pthread_cond_broadcast(&G.nonfull);
+  pthread_mutex_unlock(&G.mu);
+  pthread_join(G.worker, NULL); /* the worker drains what is queued before leaving */
+  atomic_store(&G.running, 0);
+  youth_cuda_destroy(G.h);
+  G.h = NULL;
+  youth_cuda_host_free(G.ring);
+  free(G.ts);
+  G.ring = NULL;
+  G.ts = NULL;
+}
+
+int processSlamFrame(const int16_t* depth_data, const uint8_t* color_data, int width, int height, uint32_t timestamp) {
+  (void)color_data; /* depth-only tracker; colour passes through the pipeline untouched */
+  if (!atomic_load(&G.running) || !G.h || !depth_data) return 0;
+  if (width != G.cfg.width || height != G.cfg.height) return 0;
+  pthread_mutex_lock(&G.mu);
+  if (G.lossless) {
+    while (G.count + G.busy >= G.qcap && !atomic_load(&G.stop_req)) pthread_cond_wait(&G.nonfull, &G.mu);
+    if (atomic_load(&G.stop_req)) {
+      pthread_mutex_unlock(&G.mu);
+      return 0;
+    }
+  } else if (G.count > QUEUE_HIGH_WATER || G.count + G.busy >= G.qcap) {
+    /* SLAM.cpp:163-167: more than 10 waiting -> drop the oldest down to 5 */
+    while (G.count > QUEUE_LOW_WATER) {
+      G.head = (G.head + 1) % G.qcap;
+      G.count--;
+      G.dropped++;
+    }
+  }
+  const int slot = (G.head + G.count) % G.qcap;
+  /* reference depth is int16_t; values >= 32768 are reinterpreted as uint16 like the
+   * CV_16UC1 view at SLAM.cpp:133 and then rejected by the depth_max gate */
+  memcpy(G.ring + frame_px() * (size_t)slot, depth_data, frame_px() * sizeof(uint16_t));
+  G.ts[slot] = timestamp;
+  G.count++;
+  G.accepted++;
+  pthread_cond_signal(&G.nonempty);
+  pthread_mutex_unlock(&G.mu);
+  return 1;
+}
+
+/* ---- additions for headless drivers (not in the reference facade) ---- */
+
+/* lossless: 1 = producer blocks instead of dropping; batch: frames per launch group.
+ * Call before initSlamModule; -1 keeps the environment/default choice. */
+void youthSlamSetOptions(int lossless, int batch) {
+  if (lossless >= 0) G.lossless = lossless ? 1 : 0;
+  if (batch >= 1) G.batch = batch > 64 ? 64 : batch;
+}
+
+/* wait until every accepted frame has been tracked */
+void youthSlamDrain(void) {
+  if (!atomic_load(&G.running)) return;
+  pthread_mutex_lock(&G.mu);
+  while (G.count > 0 || G.busy > 0) pthread_cond_wait(&G.idle, &G.mu);
+  pthread_mutex_unlock(&G.mu);
+}
+
+int youthSlamGetTrajectory(float* poses_out, uint32_t* timestamps_out, uint32_t* status_out, int max_frames) {
+  if (!atomic_load(&G.running) || !G.h) return 0;
+  int n = youth_cuda_get_trajectory(G.h, 0, 0, max_frames, poses_out, timestamps_out, status_out);
+  return n < 0 ? 0 : n;
+}
+
+void youthSlamStats(long* accepted, long* dropped, long* tracked) {
+  pthread_mutex_lock(&G.mu);
+  if (accepted) *accepted = G.accepted;
+  if (dropped) *dropped = G.dropped;
+  if (tracked) *tracked = G.tracked;
+  pthread_mutex_unlock(&G.mu);
+}
+
+int saveSlamMap(const char* map_file) {
+  if (!atomic_load(&G.running) || !G.h || !map_file) {
+    fprintf(stderr, "AlgorithmModule: not running\n");
+    return 0;
+  }
+  youthSlamDrain();
+  const int n = youth_cuda_frame_count(G.h, 0);
+  float* poses = (float*)malloc(sizeof(float) * 12 * (size_t)(n > 0 ? n : 1));
+  uint32_t* ts = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(n > 0 ? n : 1));
+  if (!poses || !ts) {
+    free(poses);
+    free(ts);
+    return 0;
+  }
+  int got = youth_cuda_get_trajectory(G.h, 0, 0, n, poses, ts, NULL);
+  if (got < 0) got = 0;
+  char path[1024];
+  snprintf(path, sizeof(path), "%s_trajectory.txt", map_file);
+  int ok = youth_tum_write(path, poses, ts, got);
+  /* key frames: first frame, then whenever the camera moved > 0.10 m or > 10 degrees */
+  int nk = 0;
+  for (int i = 0; i < got; ++i) {
+    int take = (i == 0);
+    if (!take) {
+      const float* a = poses + 12 * (size_t)nk - 12; /* last key frame (compacted in place) */
+      const float* b = poses + 12 * (size_t)i;
+      const float dx = b[3] - a[3], dy = b[7] - a[7], dz = b[11] - a[11];
+      float tr = 0.f; /* trace of Ra^T Rb */
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) tr += a[4 * r + c] * b[4 * r + c];
+      take = (dx * dx + dy * dy + dz * dz > 0.01f) || (tr < 1.0f + 2.0f * 0.98480775f);
+    }
+    if (take) {
+      memmove(poses + 12 * (size_t)nk, poses + 12 * (size_t)i, sizeof(float) * 12);
+      ts[nk] = ts[i];
+      ++nk;
+    }
+  }
+  snprintf(path, sizeof(path), "%s_keyframes.txt", map_file);
+  ok = youth_tum_write(path, poses, ts, nk) && ok;
+  free(poses);
+  free(ts);
+  return ok ? 1 : 0;
+}
+
+int isSlamModuleRunning(void) { return atomic_load(&G.running) ? 1 : 0; }
+
+int getSlamMapPoints(void) {
+  if (!atomic_load(&G.running) || !G.h) return 0;
+  return atomic_load(&G.last_inliers);
+}
+
+void resetSlam(void) {
+  if (!atomic_load(&G.running) || !G.h) return;
+  youthSlamDrain();
+  youth_cuda_reset(G.h, -1);
+  atomic_store(&G.last_inliers, 0);
+}

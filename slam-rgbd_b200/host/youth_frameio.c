@@ -1,0 +1,185 @@
+/*
+ * youth_frameio.c -- .bin record reader/writer and the mq chunk protocol.
+ *
+ * Record format (reference Youth.Source/LoggingModule/loggingModule.c:101-130 writer,
+ * :404-444 reader): FrameHeader (28 B, native endian, raw fwrite) + depth payload +
+ * colour payload; an optional terminating header with frameType = FRAME_TYPE_END_OF_FILE
+ * (loggingModule.c:223-226).  Unlike the reference reader, whose caller caps payloads at
+ * 1 MiB (loggingModule.c:528, :424-427) and therefore cannot replay 1280x960, the caps
+ * here are whatever the caller's buffers hold.
+ *
+ * Chunk protocol (reference loggingModule.c:447-485, sensorModule.c:149-210): each mq
+ * message = MessageHeader (292 B) + up to 7900 payload bytes; reassembly offset is
+ * chunkIndex * 7900 (loggingModule.c:313); a frame is complete when the last depth chunk
+ * AND the last colour chunk have been seen (loggingModule.c:354).
+ */
+#include <stdlib.h>
+#include <string.h>
+
+#include "youth_host.h"
+
+int youth_bin_write_frame(FILE* f, uint32_t frame_id, uint32_t timestamp_ms, int width, int height,
+                          const uint16_t* depth, const uint8_t* color) {
+  if (!f || !depth || width <= 0 || height <= 0 || width > 65535 || height > 65535) return 0;
+  FrameHeader h;
+  memset(&h, 0, sizeof(h)); /* also zeroes the 2 padding bytes the reference leaves undefined */
+  h.frameId = frame_id;
+  h.timestamp = timestamp_ms;
+  h.frameType = FRAME_TYPE_DEPTH_COLOR;
+  h.width = (uint16_t)width;
+  h.height = (uint16_t)height;
+  h.depthDataSize = (uint32_t)((size_t)width * height * sizeof(uint16_t));
+  h.colorDataSize = (uint32_t)((size_t)width * height * 3);
+  h.reserved = 0;
+  if (fwrite(&h, sizeof(h), 1, f) != 1) return 0;
+  if (fwrite(depth, 1, h.depthDataSize, f) != h.depthDataSize) return 0;
+  if (color) {
+    if (fwrite(color, 1, h.colorDataSize, f) != h.colorDataSize) return 0;
+  } else {
+    uint8_t row[4096];
+    memset(row, 128, sizeof(row));
+    size_t left = h.colorDataSize;
+    while (left) {
+      size_t n = left < sizeof(row) ? left : sizeof(row);
+      if (fwrite(row, 1, n, f) != n) return 0;
+      left -= n;
+    }
+  }
+  return 1;
+}
+
+int youth_bin_write_eof(FILE* f) {
+  if (!f) return 0;
+  FrameHeader h;
+  memset(&h, 0, sizeof(h));
+  h.frameType = FRAME_TYPE_END_OF_FILE;
+  return fwrite(&h, sizeof(h), 1, f) == 1;
+}
+
+int youth_bin_read_frame(FILE* f, FrameHeader* hdr, void* depth, size_t depth_cap, void* color,
+                         size_t color_cap) {
+  if (!f || !hdr || !depth) return 0;
+  if (fread(hdr, sizeof(*hdr), 1, f) != 1) return 0;
+  if (hdr->frameType == FRAME_TYPE_END_OF_FILE) return 0;
+  if (hdr->depthDataSize > depth_cap) return 0;
+  if (color && hdr->colorDataSize > color_cap) return 0;
+  if (fread(depth, 1, hdr->depthDataSize, f) != hdr->depthDataSize) return 0;
+  if (color) {
+    if (fread(color, 1, hdr->colorDataSize, f) != hdr->colorDataSize) return 0;
+  } else if (hdr->colorDataSize) {
+    if (fseek(f, (long)hdr->colorDataSize, SEEK_CUR) != 0) return 0;
+  }
+  return 1;
+}
+
+/* ------------------------------------------------------------------ chunks */
+
+int youth_chunk_count(size_t bytes) { return (int)YOUTH_CHUNKS_FOR(bytes); }
+
+size_t youth_chunk_build(void* msg, int msg_type, int frame_id, uint32_t timestamp_ms, int width,
+                         int height, const void* data, size_t data_bytes, int chunk) {
+  MessageHeader h;
+  memset(&h, 0, sizeof(h)); /* the reference playback path leaves ctrlCommand/filename as garbage */
+  const int total = youth_chunk_count(data_bytes);
+  size_t off = (size_t)chunk * YOUTH_CHUNK_PAYLOAD;
+  size_t n = 0;
+  if (data && chunk >= 0 && chunk < total) {
+    n = data_bytes - off;
+    if (n > (size_t)YOUTH_CHUNK_PAYLOAD) n = YOUTH_CHUNK_PAYLOAD;
+  }
+  h.msgType = msg_type;
+  h.width = width;
+  h.height = height;
+  h.chunkIndex = chunk;
+  h.totalChunks = total;
+  h.dataSize = (int)n;
+  h.frameId = frame_id;
+  h.timestamp = timestamp_ms;
+  memcpy(msg, &h, sizeof(h));
+  if (n) memcpy((char*)msg + sizeof(h), (const char*)data + off, n);
+  return sizeof(h) + n;
+}
+
+struct youth_reasm {
+  int width, height, frame_id;
+  uint32_t timestamp;
+  uint16_t* depth;
+  uint8_t* color;
+  size_t depth_bytes, color_bytes;
+  int got_depth, got_color;
+};
+
+youth_reasm* youth_reasm_create(void) { return (youth_reasm*)calloc(1, sizeof(youth_reasm)); }
+
+void youth_reasm_destroy(youth_reasm* r) {
+  if (!r) return;
+  free(r->depth);
+  free(r->color);
+  free(r);
+}
+
+static int reasm_resize(youth_reasm* r, int w, int h) {
+  if (w <= 0 || h <= 0 || w > 65535 || h > 65535) return 0;
+  if (w == r->width && h == r->height && r->depth) return 1;
+  free(r->depth);
+  free(r->color);
+  r->depth_bytes = (size_t)w * h * 2;
+  r->color_bytes = (size_t)w * h * 3;
+  r->depth = (uint16_t*)calloc(1, r->depth_bytes);
+  r->color = (uint8_t*)calloc(1, r->color_bytes);
+  r->width = w;
+  r->height = h;
+  return r->depth && r->color;
+}
+
+int youth_reasm_feed(youth_reasm* r, const void* msg, size_t len) {
+  if (!r || !msg || len < sizeof(MessageHeader)) return -1;
+  MessageHeader h;
+  memcpy(&h, msg, sizeof(h));
+  const char* payload = (const char*)msg + sizeof(h);
+  if (h.dataSize < 0 || (size_t)h.dataSize > len - sizeof(h)) return -1;
+  switch (h.msgType) {
+    case MSG_TYPE_METADATA:
+      if (!reasm_resize(r, h.width, h.height)) return -1;
+      r->frame_id = h.frameId;
+      r->timestamp = h.timestamp;
+      r->got_depth = r->got_color = 0;
+      return 0;
+    case MSG_TYPE_DEPTH_DATA:
+    case MSG_TYPE_COLOR_DATA: {
+      if (!r->depth) return -1;
+      const int is_depth = h.msgType == MSG_TYPE_DEPTH_DATA;
+      char* dst = is_depth ? (char*)r->depth : (char*)r->color;
+      const size_t cap = is_depth ? r->depth_bytes : r->color_bytes;
+      if (h.chunkIndex < 0) return -1;
+      const size_t off = (size_t)h.chunkIndex * YOUTH_CHUNK_PAYLOAD;
+      if (off + (size_t)h.dataSize > cap) return -1;
+      memcpy(dst + off, payload, (size_t)h.dataSize);
+      r->frame_id = h.frameId;
+      r->timestamp = h.timestamp;
+      if (h.chunkIndex == h.totalChunks - 1) {
+        if (is_depth)
+          r->got_depth = 1;
+        else
+          r->got_color = 1;
+      }
+      if (r->got_depth && r->got_color) {
+        r->got_depth = r->got_color = 0;
+        return 1;
+      }
+      return 0;
+    }
+    default:
+      return 0; /* control traffic is not ours */
+  }
+}
+
+const uint16_t* youth_reasm_depth(const youth_reasm* r) { return r ? r->depth : NULL; }
+const uint8_t* youth_reasm_color(const youth_reasm* r) { return r ? r->color : NULL; }
+void youth_reasm_info(const youth_reasm* r, int* w, int* h, int* id, uint32_t* ts) {
+  if (!r) return;
+  if (w) *w = r->width;
+  if (h) *h = r->height;
+  if (id) *id = r->frame_id;
+  if (ts) *ts = r->timestamp;
+}

@@ -1,0 +1,190 @@
+"""GPU parity: libyouth_cuda.so (through its C ABI) against the CPU oracle on the same
+seeded inputs.  Tolerances from BASELINE.json north_star: masks / pyramid counts /
+correspondence indices bit-exact, vertex+normal maps <= 1e-5 relative, poses <= 1e-4 rad
+and <= 1e-4 m.  Both sides use the same FMA-free operation sequence, so the tests first
+assert bit-equality and only report the tolerance-level comparison when that fails."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_MAP_REL = 1e-5
+TOL_POSE_RAD = 1e-4
+TOL_POSE_M = 1e-4
+
+
+def rot_angle(Ra, Rb):
+    R = Ra @ Rb.T
+    return float(np.arccos(np.clip((np.trace(R) - 1.0) / 2.0, -1.0, 1.0)))
+
+
+def assert_pose_close(pa, pb):
+    A, B = np.asarray(pa, dtype=np.float64).reshape(3, 4), np.asarray(pb, dtype=np.float64).reshape(3, 4)
+    assert np.linalg.norm(A[:, 3] - B[:, 3]) <= TOL_POSE_M
+    assert rot_angle(A[:, :3], B[:, :3]) <= TOL_POSE_RAD
+
+
+def assert_map_close(g, o):
+    if np.array_equal(g, o):
+        return
+    scale = np.maximum(np.abs(o), 1e-3)
+    assert np.max(np.abs(g - o) / scale) <= TOL_MAP_REL
+
+
+def make_tracker(pkg, **kw):
+    from slam_rgbd_b200.binding import Tracker
+
+    return Tracker(pkg.default_config(**kw))
+
+
+@pytest.mark.parametrize("bilateral", [1, 0])
+def test_preprocess_parity(pkg, oracle, small_seq, bilateral):
+    """stage 1+2: depth pyramid, pyramid sample counts, masks, vertex and normal maps."""
+    from slam_rgbd_b200 import binding as B
+
+    frames, _ = small_seq
+    trk = make_tracker(pkg, bilateral=bilateral, batch=4)
+    ocfg = oracle.config_from(trk.cfg)
+    trk.track_batch([frames[:3]])
+    for fi in range(3):
+        of = oracle.OFrame(ocfg, frames[fi])
+        for level in range(trk.cfg.levels):
+            d = trk.debug_read(B.DBG_DEPTH, fi, level)
+            assert np.array_equal(d, of.depth(level)), f"depth frame {fi} level {level}"
+            m = trk.debug_read(B.DBG_MASK, fi, level)
+            assert np.array_equal(m, of.mask(level)), f"mask frame {fi} level {level}"
+            if level > 0:
+                c = trk.debug_read(B.DBG_PYRCNT, fi, level)
+                assert np.array_equal(c, of.pyrcnt(level)), f"pyramid count frame {fi} level {level}"
+            assert_map_close(trk.debug_read(B.DBG_VERTEX, fi, level), of.vmap(level))
+            assert_map_close(trk.debug_read(B.DBG_NORMAL, fi, level), of.nmap(level))
+    trk.close()
+
+
+def test_preprocess_bit_exact(pkg, oracle, small_seq):
+    """The FMA-free contract makes the maps bit-identical, not merely within 1e-5."""
+    from slam_rgbd_b200 import binding as B
+
+    frames, _ = small_seq
+    trk = make_tracker(pkg, batch=2)
+    ocfg = oracle.config_from(trk.cfg)
+    trk.track_batch([frames[:2]])
+    of = oracle.OFrame(ocfg, frames[1])
+    for level in range(trk.cfg.levels):
+        assert np.array_equal(trk.debug_read(B.DBG_VERTEX, 1, level).view(np.uint32), of.vmap(level).view(np.uint32))
+        assert np.array_equal(trk.debug_read(B.DBG_NORMAL, 1, level).view(np.uint32), of.nmap(level).view(np.uint32))
+    trk.close()
+
+
+@pytest.mark.parametrize("ppt", [1, 2, 4, 8])
+def test_icp_sums_and_correspondences(pkg, oracle, small_seq, ppt):
+    """stage 3+4: correspondence indices (and reject codes) bit-exact; 29 sums bit-exact."""
+    frames, gt = small_seq
+    trk = make_tracker(pkg, batch=2, icp_ppt=ppt)
+    ocfg = oracle.config_from(trk.cfg)
+    trk.track_batch([frames[:2]])
+    prev, cur = oracle.OFrame(ocfg, frames[0]), oracle.OFrame(ocfg, frames[1])
+    poses = [np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], dtype=np.float32), gt[1].astype(np.float32)]
+    # a deliberately wrong pose exercises the distance / angle / out-of-image rejections
+    bad = poses[0].copy()
+    bad[3], bad[7] = 0.06, -0.04
+    poses.append(bad)
+    for level in range(trk.cfg.levels):
+        for pose in poses:
+            gs, gc = trk.debug_icp(1, level, pose)
+            os_, oc = oracle.icp_sums(ocfg, level, cur, prev, pose)
+            assert np.array_equal(gc, oc), f"correspondence map level {level}"
+            assert gs[28] == os_[28]
+            assert np.array_equal(gs.view(np.uint64), os_.view(np.uint64)), f"sums level {level}: {gs - os_}"
+    trk.close()
+
+
+def test_track_sequence_pose_parity(pkg, oracle, small_seq):
+    """stages 1-5 end to end over 6 frames: poses vs oracle within 1e-4 m / 1e-4 rad (and,
+    by construction, bit-identical), inlier count identical."""
+    frames, gt = small_seq
+    trk = make_tracker(pkg, batch=4)
+    ocfg = oracle.config_from(trk.cfg)
+    poses_g = np.concatenate([trk.track_batch([frames[:4]])[0], trk.track_batch([frames[4:6]])[0]])
+    poses_o, st_o, _ = oracle.track_sequence(ocfg, frames)
+    traj, ts, st = trk.trajectory()
+    assert np.array_equal(traj, poses_g)
+    assert np.array_equal(st, st_o)
+    for i in range(6):
+        assert_pose_close(poses_g[i], poses_o[i])
+    assert np.array_equal(poses_g.view(np.uint32), poses_o.view(np.uint32)), "poses not bit-identical"
+    # and the estimate is right: within 2 mm / 0.05 deg of the synthetic ground truth
+    for i in range(6):
+        G = gt[i].reshape(3, 4)
+        P = poses_g[i].astype(np.float64).reshape(3, 4)
+        assert np.linalg.norm(G[:, 3] - P[:, 3]) < 2e-3
+        assert rot_angle(G[:, :3], P[:, :3]) < np.radians(0.05)
+    trk.close()
+
+
+def test_streaming_equals_batched(pkg, small_seq):
+    """youth_cuda_track one frame at a time == youth_cuda_track_batch (pairs are independent)."""
+    frames, _ = small_seq
+    a = make_tracker(pkg, batch=1)
+    pa = np.stack([a.track(frames[i], ts=33 * i) for i in range(5)])
+    b = make_tracker(pkg, batch=5)
+    pb = b.track_batch([frames[:5]])[0]
+    assert np.array_equal(pa.view(np.uint32), pb.view(np.uint32))
+    assert a.last_inliers() == b.last_inliers() > 100000
+    a.close()
+    b.close()
+
+
+def test_determinism(pkg, small_seq):
+    """same input twice -> bitwise identical sums and poses (fixed-order reduction, no atomics)."""
+    frames, _ = small_seq
+    out = []
+    for _ in range(2):
+        t = make_tracker(pkg, batch=3)
+        p = t.track_batch([frames[:3]])[0]
+        s, _c = t.debug_icp(2, 0, np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], dtype=np.float32), want_corr=False)
+        out.append((p.copy(), s.copy()))
+        t.close()
+    assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32))
+    assert np.array_equal(out[0][1].view(np.uint64), out[1][1].view(np.uint64))
+
+
+def test_multi_stream_matches_single(pkg):
+    """two sequences tracked in one handle == each tracked alone."""
+    fa, fb = pkg.synth_sequence(4, sequence=0), pkg.synth_sequence(4, sequence=5)
+    both = make_tracker(pkg, n_streams=2, batch=4)
+    pboth = both.track_batch([fa, fb])
+    for k, f in enumerate((fa, fb)):
+        one = make_tracker(pkg, batch=4)
+        p = one.track_batch([f])[0]
+        assert np.array_equal(p.view(np.uint32), pboth[k].view(np.uint32))
+        one.close()
+    both.close()
+
+
+def test_edge_cases(pkg, oracle):
+    """empty (all-invalid) frames, a frame with no overlap, reset, and capacity errors."""
+    from slam_rgbd_b200 import binding as B
+
+    trk = make_tracker(pkg, batch=2, traj_capacity=5)
+    ocfg = oracle.config_from(trk.cfg)
+    H, W = trk.cfg.height, trk.cfg.width
+    empty = np.zeros((2, H, W), dtype=np.uint16)
+    p = trk.track_batch([empty])[0]
+    ident = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], dtype=np.float32)
+    assert np.array_equal(p[0], ident) and np.array_equal(p[1], ident)
+    _, _, st = trk.trajectory()
+    assert st[0] == B.STATUS_FIRST and st[1] == B.STATUS_LOST  # no inliers -> pose kept, flagged
+    po, so, _ = oracle.track_sequence(ocfg, empty)
+    assert np.array_equal(po, p) and np.array_equal(so, st)
+    assert trk.last_inliers() == 0
+    # maximum raw values are outside the depth gate -> invalid everywhere
+    full = np.full((2, H, W), 65535, dtype=np.uint16)
+    trk.track_batch([full])
+    assert not trk.debug_read(B.DBG_MASK, 3, 0).any()
+    with pytest.raises(RuntimeError):  # capacity 5: frames 4,5 do not fit
+        trk.track_batch([empty])
+    trk.reset()
+    assert trk.frame_count() == 0
+    assert np.array_equal(trk.track_batch([empty[:1]])[0][0], ident)
+    trk.close()
