@@ -14,8 +14,9 @@ TOL_POSE_M = 1e-4
 
 
 def rot_angle(Ra, Rb):
-    R = Ra @ Rb.T
-    return float(np.arccos(np.clip((np.trace(R) - 1.0) / 2.0, -1.0, 1.0)))
+    """Angle between two rotations; chordal form, well conditioned near zero
+    (|Ra - Rb|_F = 2*sqrt(2)*sin(angle/2)), unlike arccos of the trace."""
+    return float(2.0 * np.arcsin(min(1.0, np.linalg.norm(Ra - Rb) / (2.0 * np.sqrt(2.0)))))
 
 
 def assert_pose_close(pa, pb):
