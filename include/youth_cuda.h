@@ -140,6 +140,18 @@ int youth_cuda_debug_icp(youth_cuda_handle* h, int stream, int frame, int level,
 int youth_cuda_timer_start(youth_cuda_handle* h);
 int youth_cuda_timer_stop(youth_cuda_handle* h, float* ms_out);
 
+/* Per-kernel-class device timing: while enabled every launch is bracketed by CUDA events on
+ * the launching stream (serialises nothing, but adds event records, so throughput numbers
+ * are taken with it off).  ms_out / launches_out: [YOUTH_PROF_CLASSES] totals since enable. */
+#define YOUTH_PROF_INGEST 0  /* k_ingest: depth ingest + bilateral + pyramid + vertex maps */
+#define YOUTH_PROF_NORMALS 1 /* k_normals */
+#define YOUTH_PROF_ICP0 2    /* k_icp at level 0 (ICP0 + l = level l) */
+#define YOUTH_PROF_SOLVE 6   /* unused since the solve moved into k_icp's last tile */
+#define YOUTH_PROF_MISC 7    /* k_compose */
+#define YOUTH_PROF_CLASSES 8
+int youth_cuda_profile_enable(youth_cuda_handle* h, int on);
+int youth_cuda_profile_read(youth_cuda_handle* h, double* ms_out, uint64_t* launches_out);
+
 /* Kernels launched by this handle since init (for bench.py's gpu_launches). */
 uint64_t youth_cuda_launch_count(youth_cuda_handle* h);
 

@@ -49,7 +49,22 @@ def build(force=False):
 _libs = {}
 
 
+def fast_supported():
+    """The speed build uses AVX2+FMA; only load it on hosts that have both."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    flags = set(line.split(":", 1)[1].split())
+                    return "avx2" in flags and "fma" in flags
+    except OSError:
+        pass
+    return False
+
+
 def lib(fast=False):
+    if fast and not fast_supported():
+        raise RuntimeError("host CPU lacks AVX2/FMA: speed build of the oracle not usable")
     key = "fast" if fast else "parity"
     if key in _libs:
         return _libs[key]

@@ -11,6 +11,7 @@ SUM_SLOTS = 32
 MEM_HOST, MEM_DEVICE, MEM_HOST_PINNED = 0, 1, 2
 DBG_DEPTH, DBG_VERTEX, DBG_NORMAL, DBG_MASK, DBG_PYRCNT = 1, 2, 3, 4, 5
 STATUS_FIRST, STATUS_LOST = 1, 2
+PROF_INGEST, PROF_NORMALS, PROF_ICP0, PROF_SOLVE, PROF_MISC, PROF_CLASSES = 0, 1, 2, 6, 7, 8
 
 
 class CudaLibraryMissing(RuntimeError):
@@ -57,7 +58,8 @@ class SynthConfig(C.Structure):
 
 def lib_paths():
     return {
-        "cuda": os.path.join(PKG_DIR, "lib", "libyouth_cuda.so"),
+        # YOUTH_CUDA_LIB: A/B builds of the same source (tools/ only); never a non-CUDA substitute
+        "cuda": os.environ.get("YOUTH_CUDA_LIB") or os.path.join(PKG_DIR, "lib", "libyouth_cuda.so"),
         "host": os.path.join(PKG_DIR, "lib", "libAlgorithmModule.so"),
         "harness": os.path.join(PKG_DIR, "bin", "youth_harness"),
     }
@@ -99,6 +101,8 @@ def cuda_lib():
         "youth_cuda_timer_start": (C.c_int, [H]),
         "youth_cuda_timer_stop": (C.c_int, [H, C.POINTER(C.c_float)]),
         "youth_cuda_launch_count": (C.c_uint64, [H]),
+        "youth_cuda_profile_enable": (C.c_int, [H, C.c_int]),
+        "youth_cuda_profile_read": (C.c_int, [H, C.c_void_p, C.c_void_p]),
         "youth_cuda_last_error": (C.c_char_p, []),
         "youth_cuda_abi_version": (C.c_int, []),
     }
@@ -300,6 +304,15 @@ class Tracker:
         ms = C.c_float()
         self._check(self.lib.youth_cuda_timer_stop(self.h, C.byref(ms)), "youth_cuda_timer_stop")
         return ms.value
+
+    def profile(self, on):
+        self._check(self.lib.youth_cuda_profile_enable(self.h, 1 if on else 0), "youth_cuda_profile_enable")
+
+    def profile_read(self):
+        ms = np.zeros(PROF_CLASSES, dtype=np.float64)
+        n = np.zeros(PROF_CLASSES, dtype=np.uint64)
+        self._check(self.lib.youth_cuda_profile_read(self.h, ms.ctypes.data, n.ctypes.data), "youth_cuda_profile_read")
+        return ms, n
 
     def launch_count(self):
         return int(self.lib.youth_cuda_launch_count(self.h))

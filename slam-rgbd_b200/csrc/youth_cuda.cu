@@ -76,6 +76,7 @@ struct youth_cuda_handle {
   float* partials;
   double* sums;
   uint32_t* pair_status;
+  unsigned int* tickets;
   /* sequence state */
   int* seq_count;
   double* world;
@@ -88,7 +89,43 @@ struct youth_cuda_handle {
   int32_t* corr_dbg; /* debug correspondence map (level-0 sized) */
   cudaEvent_t t0, t1;
   uint64_t launches;
+  /* per-kernel-class event timing (youth_cuda_profile_*): off on the normal path */
+  bool prof_on;
+  cudaEvent_t* prof_ev; /* pairs: [2*i] before, [2*i+1] after launch i */
+  int* prof_cls;
+  int prof_n, prof_cap;
+  double prof_ms[YOUTH_PROF_CLASSES];
+  uint64_t prof_launches[YOUTH_PROF_CLASSES];
 };
+
+/* bracket one launch with events when profiling is on */
+struct ProfScope {
+  youth_cuda_handle* h;
+  int idx;
+  ProfScope(youth_cuda_handle* hh, int cls) : h(hh), idx(-1) {
+    h->launches++;
+    if (!h->prof_on || h->prof_n >= h->prof_cap) return;
+    idx = h->prof_n++;
+    h->prof_cls[idx] = cls;
+    cudaEventRecord(h->prof_ev[2 * idx], h->stream);
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(h->prof_ev[2 * idx + 1], h->stream);
+  }
+};
+
+static int prof_flush(youth_cuda_handle* h) {
+  if (h->prof_n == 0) return 1;
+  CU(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < h->prof_n; ++i) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+    h->prof_ms[h->prof_cls[i]] += (double)ms;
+    h->prof_launches[h->prof_cls[i]]++;
+  }
+  h->prof_n = 0;
+  return 1;
+}
 
 extern "C" int youth_cuda_default_config(youth_cuda_config* c) {
   if (!c) return fail("null config");
@@ -171,12 +208,18 @@ extern "C" void youth_cuda_destroy(youth_cuda_handle* h) {
   cudaFree(h->partials);
   cudaFree(h->sums);
   cudaFree(h->pair_status);
+  cudaFree(h->tickets);
   cudaFree(h->seq_count);
   cudaFree(h->world);
   cudaFree(h->traj);
   cudaFree(h->traj_status);
   cudaFree(h->last_inliers);
   cudaFree(h->corr_dbg);
+  if (h->prof_ev) {
+    for (int i = 0; i < 2 * h->prof_cap; ++i) cudaEventDestroy(h->prof_ev[i]);
+    free(h->prof_ev);
+    free(h->prof_cls);
+  }
   if (h->t0) cudaEventDestroy(h->t0);
   if (h->t1) cudaEventDestroy(h->t1);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -265,6 +308,7 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
   CU(dalloc(&h->partials, (size_t)h->P * h->max_tiles * 32));
   CU(dalloc(&h->sums, (size_t)h->P * 32));
   CU(dalloc(&h->pair_status, (size_t)h->P));
+  CU(dalloc(&h->tickets, (size_t)h->P));
   CU(dalloc(&h->seq_count, (size_t)h->S));
   CU(dalloc(&h->world, (size_t)h->S * 12));
   CU(dalloc(&h->traj, (size_t)h->S * cfg->traj_capacity * 12));
@@ -309,14 +353,14 @@ static RingGeom ring_of(const youth_cuda_handle* h, int n) {
 }
 
 template <bool DEBUG>
-static void launch_icp(youth_cuda_handle* h, const IcpParams& ip, dim3 grid) {
+static void launch_icp(youth_cuda_handle* h, const IcpParams& ip, dim3 grid, int level) {
+  ProfScope ps(h, YOUTH_PROF_ICP0 + level);
   switch (h->cfg.icp_ppt) {
     case 1: k_icp<1, DEBUG><<<grid, YOUTH_ICP_THREADS, 0, h->stream>>>(ip); break;
     case 2: k_icp<2, DEBUG><<<grid, YOUTH_ICP_THREADS, 0, h->stream>>>(ip); break;
     case 4: k_icp<4, DEBUG><<<grid, YOUTH_ICP_THREADS, 0, h->stream>>>(ip); break;
     default: k_icp<8, DEBUG><<<grid, YOUTH_ICP_THREADS, 0, h->stream>>>(ip); break;
   }
-  h->launches++;
 }
 
 static IcpParams icp_params(const youth_cuda_handle* h, int level, const RingGeom& ring) {
@@ -338,6 +382,13 @@ static IcpParams icp_params(const youth_cuda_handle* h, int level, const RingGeo
   ip.dbg_cur_slot = -1;
   ip.dbg_prev_slot = -1;
   ip.dbg_stream = 0;
+  ip.tickets = h->tickets;
+  ip.pose_d = h->pose_d;
+  ip.pose_f_out = h->pose_f;
+  ip.sums = h->sums;
+  ip.pair_status = h->pair_status;
+  ip.min_inliers = h->cfg.min_inliers;
+  ip.do_solve = 1;
   return ip;
 }
 
@@ -357,6 +408,9 @@ static int enqueue_group(youth_cuda_handle* h, const uint16_t* const* raw_dev, i
       ip.pyrcnt[l] = h->pyrcnt[l];
       ip.lv[l] = h->lv[l];
     }
+    ip.pose_d = h->pose_d;
+    ip.pose_f = h->pose_f;
+    ip.pair_status = h->pair_status;
     ip.ring = ring;
     ip.levels = c.levels;
     ip.dmin = c.depth_min_mm;
@@ -367,11 +421,11 @@ static int enqueue_group(youth_cuda_handle* h, const uint16_t* const* raw_dev, i
     ip.depth_factor = c.depth_factor;
     ip.pyr_thr = 3.0f * c.sigma_range_mm;
     dim3 grid((c.width + YK_TILE_W - 1) / YK_TILE_W, (c.height + YK_TILE_H - 1) / YK_TILE_H, frames);
+    ProfScope ps(h, YOUTH_PROF_INGEST);
     if (c.bilateral)
       k_ingest<true><<<grid, 256, 0, h->stream>>>(ip);
     else
       k_ingest<false><<<grid, 256, 0, h->stream>>>(ip);
-    h->launches++;
   }
   /* stage 2b */
   {
@@ -387,32 +441,13 @@ static int enqueue_group(youth_cuda_handle* h, const uint16_t* const* raw_dev, i
     np.ring = ring;
     np.levels = c.levels;
     dim3 grid((total + 255) / 256, frames);
+    ProfScope ps(h, YOUTH_PROF_NORMALS);
     k_normals<<<grid, 256, 0, h->stream>>>(np);
-    h->launches++;
   }
-  /* stages 3-5: coarse to fine, fixed iteration schedule, no host sync */
-  k_init_pairs<<<(frames + 127) / 128, 128, 0, h->stream>>>(frames, h->pose_d, h->pose_f, h->pair_status);
-  h->launches++;
-  SolveParams sp;
-  memset(&sp, 0, sizeof(sp));
-  sp.partials = h->partials;
-  sp.max_tiles = h->max_tiles;
-  sp.ring = ring;
-  sp.seq_count = h->seq_count;
-  sp.pose_d = h->pose_d;
-  sp.pose_f = h->pose_f;
-  sp.sums = h->sums;
-  sp.pair_status = h->pair_status;
-  sp.min_inliers = c.min_inliers;
-  sp.do_solve = 1;
+  /* stages 3-5: coarse to fine, fixed iteration schedule, one launch per iteration, no host sync */
   for (int level = c.levels - 1; level >= 0; --level) {
     const IcpParams ip = icp_params(h, level, ring);
-    sp.ntiles = h->ntiles[level];
-    for (int it = 0; it < c.iters[level]; ++it) {
-      launch_icp<false>(h, ip, dim3(h->ntiles[level], frames));
-      k_solve<<<frames, 256, 0, h->stream>>>(sp);
-      h->launches++;
-    }
+    for (int it = 0; it < c.iters[level]; ++it) launch_icp<false>(h, ip, dim3(h->ntiles[level], frames), level);
   }
   /* pose chain + trajectory append */
   {
@@ -428,10 +463,11 @@ static int enqueue_group(youth_cuda_handle* h, const uint16_t* const* raw_dev, i
     cp.traj_status = h->traj_status;
     cp.last_inliers = h->last_inliers;
     cp.cap = c.traj_capacity;
+    ProfScope ps(h, YOUTH_PROF_MISC);
     k_compose<<<(h->S + 63) / 64, 64, 0, h->stream>>>(cp);
-    h->launches++;
   }
   CU(cudaGetLastError());
+  if (h->prof_on && h->prof_n > h->prof_cap - 256) return prof_flush(h);
   return 1;
 }
 
@@ -520,8 +556,7 @@ extern "C" int youth_cuda_reset(youth_cuda_handle* h, int stream) {
     CU(cudaMemsetAsync(h->seq_count, 0, sizeof(int) * h->S, h->stream));
     CU(cudaMemsetAsync(h->last_inliers, 0, sizeof(int) * h->S, h->stream));
     memset(h->h_count, 0, sizeof(int) * h->S);
-    CU(cudaStreamSynchronize(h->stream));
-    h->total = 0;
+    h->total = 0; /* stream-ordered: later groups see the cleared counters */
   } else {
     CU(cudaMemsetAsync(h->seq_count + stream, 0, sizeof(int), h->stream));
     CU(cudaMemsetAsync(h->last_inliers + stream, 0, sizeof(int), h->stream));
@@ -654,22 +689,8 @@ extern "C" int youth_cuda_debug_icp(youth_cuda_handle* h, int stream, int frame,
   ip.dbg_cur_slot = cur;
   ip.dbg_prev_slot = prev;
   ip.dbg_stream = stream;
-  launch_icp<true>(h, ip, dim3(h->ntiles[level], 1));
-  SolveParams sp;
-  memset(&sp, 0, sizeof(sp));
-  sp.partials = h->partials;
-  sp.ntiles = h->ntiles[level];
-  sp.max_tiles = h->max_tiles;
-  sp.ring = ring;
-  sp.seq_count = h->seq_count;
-  sp.pose_d = h->pose_d;
-  sp.pose_f = h->pose_f;
-  sp.sums = h->sums;
-  sp.pair_status = h->pair_status;
-  sp.min_inliers = h->cfg.min_inliers;
-  sp.do_solve = 0;
-  k_solve<<<1, 256, 0, h->stream>>>(sp);
-  h->launches++;
+  ip.do_solve = 0;
+  launch_icp<true>(h, ip, dim3(h->ntiles[level], 1), level);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(sums_out, h->sums, sizeof(double) * 32, cudaMemcpyDeviceToHost, h->stream));
   if (corr_out)
@@ -695,3 +716,34 @@ extern "C" int youth_cuda_timer_stop(youth_cuda_handle* h, float* ms_out) {
 }
 
 extern "C" uint64_t youth_cuda_launch_count(youth_cuda_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int youth_cuda_profile_enable(youth_cuda_handle* h, int on) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  if (on && !h->prof_ev) {
+    h->prof_cap = 4096;
+    h->prof_ev = (cudaEvent_t*)calloc((size_t)2 * h->prof_cap, sizeof(cudaEvent_t));
+    h->prof_cls = (int*)calloc((size_t)h->prof_cap, sizeof(int));
+    if (!h->prof_ev || !h->prof_cls) return fail("host allocation failed");
+    for (int i = 0; i < 2 * h->prof_cap; ++i) CU(cudaEventCreate(&h->prof_ev[i]));
+  }
+  if (!on && h->prof_on && !prof_flush(h)) return 0;
+  if (on && !h->prof_on) {
+    memset(h->prof_ms, 0, sizeof(h->prof_ms));
+    memset(h->prof_launches, 0, sizeof(h->prof_launches));
+    h->prof_n = 0;
+  }
+  h->prof_on = on != 0;
+  return 1;
+}
+
+extern "C" int youth_cuda_profile_read(youth_cuda_handle* h, double* ms_out, uint64_t* launches_out) {
+  if (!h || !ms_out || !launches_out) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  if (!prof_flush(h)) return 0;
+  for (int i = 0; i < YOUTH_PROF_CLASSES; ++i) {
+    ms_out[i] = h->prof_ms[i];
+    launches_out[i] = h->prof_launches[i];
+  }
+  return 1;
+}
