@@ -431,27 +431,32 @@ int yo_solve_update(const yo_config* c, const double* sums, double pose_d[12], f
   double scale = A[0][0];
   for (int i = 1; i < 6; ++i)
     if (A[i][i] > scale) scale = A[i][i];
+  /* Cholesky A = L L^T with one reciprocal per column (divisions by the pivot become
+   * multiplications), forward substitution in ascending and back substitution in
+   * DESCENDING column order -- the order a row-per-lane device solve produces naturally. */
+  double inv[6];
   memset(L, 0, sizeof(L));
   for (int j = 0; j < 6; ++j) {
     double d = A[j][j];
     for (int m = 0; m < j; ++m) d = d - L[j][m] * L[j][m];
     if (!(d > 1e-12 * scale)) return 0;
     L[j][j] = sqrt(d);
+    inv[j] = 1.0 / L[j][j];
     for (int i = j + 1; i < 6; ++i) {
       double s = A[i][j];
       for (int m = 0; m < j; ++m) s = s - L[i][m] * L[j][m];
-      L[i][j] = s / L[j][j];
+      L[i][j] = s * inv[j];
     }
   }
   for (int i = 0; i < 6; ++i) {
     double s = b[i];
     for (int m = 0; m < i; ++m) s = s - L[i][m] * yv[m];
-    yv[i] = s / L[i][i];
+    yv[i] = s * inv[i];
   }
   for (int i = 5; i >= 0; --i) {
     double s = yv[i];
-    for (int m = i + 1; m < 6; ++m) s = s - L[m][i] * x[m];
-    x[i] = s / L[i][i];
+    for (int m = 5; m > i; --m) s = s - L[m][i] * x[m];
+    x[i] = s * inv[i];
   }
   for (int i = 0; i < 6; ++i)
     if (!(x[i] > -1e6 && x[i] < 1e6)) return 0; /* also rejects NaN */

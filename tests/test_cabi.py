@@ -1,0 +1,168 @@
+"""The drop-in boundary on a machine without a GPU: every function declared in include/*.h
+is exported by the library that owns it, structs mirror the headers, configuration and
+trajectory egress behave, and the compute entry points FAIL LOUDLY (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+from scipy.spatial.transform import Rotation
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INC = os.path.join(ROOT, "include")
+
+DECL = re.compile(r"^[A-Za-z_][\w\s\*]*?\b(\w+)\s*\([^;{]*\)\s*;", re.M | re.S)
+
+
+def declared_functions(header):
+    src = open(os.path.join(INC, header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
+    src = re.sub(r"typedef struct[^;]*?\{.*?\}\s*\w+;", "", src, flags=re.S)
+    names = [m.group(1) for m in DECL.finditer(src)]
+    return [n for n in names if n not in ("YOUTH_STATIC_ASSERT",)]
+
+
+def gpu_present():
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_cuda_library_exports_every_declared_symbol(pkg):
+    names = declared_functions("youth_cuda.h")
+    assert len(names) >= 20 and "youth_cuda_init" in names and "youth_cuda_track_batch" in names
+    lib = C.CDLL(pkg.lib_paths()["cuda"])
+    for n in names:
+        assert hasattr(lib, n), f"libyouth_cuda.so does not export {n}"
+    assert lib.youth_cuda_abi_version() == 1
+
+
+def test_facade_library_exports_reference_entry_points(pkg):
+    lib = C.CDLL(pkg.lib_paths()["host"])
+    facade = declared_functions("SLAM.h") + declared_functions("algorithmModule.h")
+    # exactly the reference's exported C symbols (SLAM.h:11-38, algorithmModule.h:6)
+    assert sorted(facade) == sorted(["initSlamModule", "stopSlamModule", "processSlamFrame", "saveSlamMap",
+                                     "isSlamModuleRunning", "getSlamMapPoints", "resetSlam", "algorithmModule"])
+    for n in facade + declared_functions("youth_host.h"):
+        assert hasattr(lib, n), f"libAlgorithmModule.so does not export {n}"
+
+
+def test_config_struct_mirrors_header(pkg):
+    from slam_rgbd_b200.binding import YouthConfig
+
+    cfg = pkg.default_config()
+    assert C.sizeof(YouthConfig) == 112  # 26 x 4-byte fields + pointer, 8-byte aligned
+    assert (cfg.width, cfg.height, cfg.levels, list(cfg.iters)[:3]) == (640, 480, 3, [10, 5, 4])
+    assert np.float32(cfg.fx) == np.float32(570.3) and cfg.cx == 320.0 and cfg.cy == 240.0
+    assert cfg.depth_factor == 1000.0 and cfg.bilateral == 1 and cfg.icp_ppt == 4
+
+
+def test_oracle_and_product_defaults_agree(pkg, oracle):
+    a, b = pkg.default_config(), oracle.default_config()
+    for name, _ in oracle.OracleConfig._fields_:
+        va, vb = getattr(a, name), getattr(b, name)
+        assert (list(va) == list(vb)) if name == "iters" else (va == vb), name
+
+
+def test_yaml_config(pkg, tmp_path):
+    from slam_rgbd_b200.binding import YouthConfig
+
+    host = pkg.host_lib()
+    y = tmp_path / "cam.yaml"
+    y.write_text('%YAML:1.0\n# comment\nCamera.type: "PinHole"\nCamera.fx: 525.5\nCamera.fy: 526.5\n'
+                 "Camera.cx: 319.5\nCamera.cy: 239.5\nCamera.k1: 0.0\nCamera.width: 320\nCamera.height: 240\n"
+                 "Camera.fps: 30.0\nDepthMapFactor: 5000.0\nORBextractor.nFeatures: 1000\n")
+    cfg = YouthConfig()
+    assert host.youth_config_from_yaml(str(y).encode(), C.byref(cfg)) == 1
+    assert (cfg.width, cfg.height) == (320, 240)
+    assert np.float32(cfg.fx) == np.float32(525.5) and np.float32(cfg.fy) == np.float32(526.5)
+    assert cfg.cx == 319.5 and cfg.cy == 239.5 and cfg.depth_factor == 5000.0
+    assert cfg.levels == 3  # untouched keys keep their defaults
+    assert host.youth_config_from_yaml(None, C.byref(cfg)) == 1 and cfg.width == 640
+    assert host.youth_config_from_yaml(b"/nonexistent/file.yaml", C.byref(cfg)) == 0
+
+
+def test_tum_writer_and_quaternion(pkg, tmp_path):
+    host = pkg.host_lib()
+    rng = np.random.default_rng(1)
+    rots = Rotation.from_rotvec(rng.normal(size=(12, 3)) * np.array([0.1, 1.0, 3.0, 0.5] * 3)[:, None])
+    poses = np.zeros((12, 12), dtype=np.float32)
+    for i, R in enumerate(rots.as_matrix()):
+        poses[i] = np.concatenate([R, rng.normal(size=(3, 1))], axis=1).reshape(12)
+    ts = (np.arange(12) * 33).astype(np.uint32)
+    p = tmp_path / "t.txt"
+    assert host.youth_tum_write(str(p).encode(), poses.ctypes.data, ts.ctypes.data, 12) == 1
+    rows = np.loadtxt(p)
+    assert rows.shape == (12, 8)
+    assert np.allclose(rows[:, 0], ts / 1000.0)
+    assert np.allclose(rows[:, 1:4], poses[:, [3, 7, 11]], atol=1e-6)
+    q = rots.as_quat()  # x y z w
+    for i in range(12):  # q and -q are the same rotation
+        assert min(np.abs(rows[i, 4:] - q[i]).max(), np.abs(rows[i, 4:] + q[i]).max()) < 1e-5
+
+
+def test_synth_generator_is_deterministic_and_shaped(pkg):
+    a = pkg.synth_sequence(2, 160, 120, sequence=2)
+    b = pkg.synth_sequence(2, 160, 120, sequence=2)
+    assert np.array_equal(a, b)
+    assert a.dtype == np.uint16 and a.shape == (2, 120, 160)
+    holes = (a == 0).mean()
+    assert 0.01 < holes < 0.04  # 2 % hashed dropout
+    assert a[a > 0].min() >= 600 and a.max() <= 8000
+    assert not np.array_equal(a, pkg.synth_sequence(2, 160, 120, sequence=3))
+    n = pkg.synth_sequence(1, 160, 120, sequence=2, noise=1)
+    d = n[0].astype(int) - a[0].astype(int)
+    both = (n[0] > 0) & (a[0] > 0)
+    assert np.abs(d[both]).max() <= 2 and np.abs(d[both]).max() > 0
+    gt = pkg.synth_gt(3, 160, 120, sequence=2)
+    assert np.allclose(gt[0], [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], atol=1e-12)
+    R = gt[2].reshape(3, 4)[:, :3]
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-12)
+
+
+@pytest.mark.skipif(gpu_present(), reason="exercises the no-GPU failure path")
+def test_compute_entry_points_fail_loudly_without_gpu(pkg):
+    from slam_rgbd_b200.binding import Tracker
+
+    with pytest.raises(RuntimeError, match="no CUDA device|no CPU fallback|failed"):
+        Tracker(pkg.default_config())
+    host = pkg.host_lib()
+    host.initSlamModule(None, None)
+    assert host.isSlamModuleRunning() == 0
+    frame = np.zeros((480, 640), dtype=np.uint16)
+    assert host.processSlamFrame(frame.ctypes.data, None, 640, 480, 0) == 0
+    assert host.saveSlamMap(b"/tmp/should_not_exist") == 0
+    assert host.getSlamMapPoints() == 0
+    host.resetSlam()
+    host.stopSlamModule()
+
+
+def test_init_rejects_bad_configs(pkg):
+    from slam_rgbd_b200.binding import Tracker
+
+    for kw in (dict(levels=0), dict(levels=5), dict(width=641), dict(height=481, levels=3), dict(icp_ppt=3),
+               dict(n_streams=0), dict(batch=0), dict(depth_min_mm=0), dict(depth_max_mm=70000), dict(fx=0.0)):
+        with pytest.raises(RuntimeError):
+            Tracker(pkg.default_config(**kw))
+
+
+def test_product_never_references_the_oracle():
+    """the oracle is test infrastructure: nothing under slam-rgbd_b200/ or include/ may
+    include, link or import it."""
+    bad = []
+    for base in ("slam-rgbd_b200", "include"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".c", ".cu", ".cuh", ".h", ".py", "Makefile", ".txt")):
+                    txt = open(os.path.join(dp, f), errors="ignore").read()
+                    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)            # C comments may cite the spec
+                    txt = re.sub(r'""".*?"""', "", txt, flags=re.S)             # so may docstrings
+                    txt = re.sub(r"(^|\s)(//|#(?!include)).*$", "", txt, flags=re.M)
+                    if re.search(r"oracle|yo_track|yo_icp", txt):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad

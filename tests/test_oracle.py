@@ -1,0 +1,251 @@
+"""CPU oracle: known-answer tests with closed-form results, the conventions the reference
+pins (depth unit, validity, pinhole back-projection: ViewerModule/viewerModule.c:341-345;
+intrinsics: config/astra_orb_slam3_rgbd.yaml:9-12), independent numpy/scipy cross-checks of
+the solve and the reduction, and the committed golden fixture."""
+import ctypes as C
+import hashlib
+import os
+
+import numpy as np
+import pytest
+from scipy.spatial.transform import Rotation
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+IDENT = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], dtype=np.float32)
+
+
+def small_cfg(O, w=160, h=120, **kw):
+    return O.default_config(width=w, height=h, fx=570.3 * w / 640, fy=570.3 * w / 640, cx=w / 2.0, cy=h / 2.0, **kw)
+
+
+def test_defaults_match_reference_yaml(oracle):
+    cfg = oracle.default_config()
+    assert (cfg.width, cfg.height) == (640, 480)
+    assert np.float32(cfg.fx) == np.float32(570.3) and np.float32(cfg.fy) == np.float32(570.3)
+    assert (cfg.cx, cfg.cy, cfg.depth_factor) == (320.0, 240.0, 1000.0)
+    assert list(cfg.iters)[:3] == [10, 5, 4] and cfg.levels == 3
+
+
+def test_level_geometry(oracle):
+    cfg = oracle.default_config()
+    g1, g2 = oracle.level_geometry(cfg, 1), oracle.level_geometry(cfg, 2)
+    assert (g1.w, g1.h, g2.w, g2.h) == (320, 240, 160, 120)
+    assert g1.fx == np.float32(570.3) / 2 and g2.fx == np.float32(570.3) / 4
+    assert g1.cx == (320.0 - 0.5) / 2 and g2.cx == ((320.0 - 0.5) / 2 - 0.5) / 2
+
+
+def test_backprojection_follows_viewer_formula(oracle):
+    """restatement of viewerModule.c:341-345 in numpy float32: valid iff depth > 0,
+    z = d / 1000, x = (u - W/2) * z / 570.3, y = (v - H/2) * z / 570.3."""
+    cfg = oracle.default_config(bilateral=0, levels=1)
+    rng = np.random.default_rng(3)
+    raw = rng.integers(0, 6000, size=(480, 640), dtype=np.uint16)
+    raw[rng.random(raw.shape) < 0.1] = 0
+    f = oracle.OFrame(cfg, raw)
+    v = f.vmap(0)
+    u, vv = np.meshgrid(np.arange(640, dtype=np.float32), np.arange(480, dtype=np.float32))
+    z = raw.astype(np.float32) / np.float32(1000.0)
+    x = (u - np.float32(640 // 2)) * z / np.float32(570.3)
+    y = (vv - np.float32(480 // 2)) * z / np.float32(570.3)
+    valid = raw > 0
+    assert np.array_equal(v[..., 3] == 1.0, valid)
+    assert np.array_equal(v[..., 0][valid], x[valid])
+    assert np.array_equal(v[..., 1][valid], y[valid])
+    assert np.array_equal(v[..., 2][valid], z[valid])
+    assert not v[~valid].any()
+
+
+def test_plane_normals_and_validity(oracle):
+    cfg = small_cfg(oracle)
+    raw = np.full((120, 160), 1000, dtype=np.uint16)
+    raw[40:43, 70:75] = 0  # a hole
+    f = oracle.OFrame(cfg, raw)
+    for level in range(3):
+        n, v = f.nmap(level), f.vmap(level)
+        ok = n[..., 3] == 1.0
+        assert np.allclose(n[ok][:, :3], [0, 0, 1], atol=1e-4)  # fronto-parallel plane, forward differences
+        assert not ok[-1, :].any() and not ok[:, -1].any()      # last row/column have no forward neighbour
+        assert np.allclose(v[..., 2][v[..., 3] == 1.0], 1.0, rtol=1e-6)
+    # a normal needs its right and lower neighbours: the hole invalidates one pixel up/left too
+    m = f.mask(0)
+    assert not (m[40:43, 70:75] & 1).any()
+    assert not (m[40:43, 69] & 2).any() and not (m[39, 70:75] & 2).any()
+    assert (m[38, 70:75] == 3).all()
+
+
+def test_depth_gate_and_bilateral_properties(oracle):
+    cfg = small_cfg(oracle, depth_min_mm=500, depth_max_mm=4000)
+    raw = np.full((120, 160), 2000, dtype=np.uint16)
+    raw[:10] = 100     # below the gate
+    raw[-10:] = 60000  # above the gate
+    raw[50:70, 80:] = 2500  # a 500 mm step: far beyond 3 sigma_r = 90 mm, must stay sharp
+    d0 = np.empty((120, 160), dtype=np.float32)
+    oracle.lib().yo_bilateral(C.byref(cfg), raw.ctypes.data, d0.ctypes.data)
+    assert not d0[:10].any() and not d0[-10:].any()
+    assert np.allclose(d0[10:50], 2000.0, rtol=1e-6)  # constant regions are fixed points (up to float rounding)
+    assert np.allclose(d0[50:70, :80], 2000.0, rtol=1e-6) and np.allclose(d0[50:70, 80:], 2500.0, rtol=1e-6)
+    # smoothing: +-2 mm noise is reduced
+    rng = np.random.default_rng(0)
+    noisy = (2000 + rng.integers(-2, 3, size=(120, 160))).astype(np.uint16)
+    oracle.lib().yo_bilateral(C.byref(cfg), noisy.ctypes.data, d0.ctypes.data)
+    assert d0[20:100, 20:140].std() < 0.5 * noisy[20:100, 20:140].astype(np.float64).std()
+    cfg.bilateral = 0
+    oracle.lib().yo_bilateral(C.byref(cfg), noisy.ctypes.data, d0.ctypes.data)
+    assert np.array_equal(d0, noisy.astype(np.float32))
+
+
+def test_pyrdown_rule(oracle):
+    cfg = small_cfg(oracle)
+    src = np.zeros((4, 8), dtype=np.float32)
+    src[0:2, 0:2] = [[1000, 1010], [1020, 1030]]   # all within 90 mm -> mean of 4
+    src[0:2, 2:4] = [[0, 1000], [1200, 1010]]      # first valid is 1000; 1200 is outside the gate
+    src[0:2, 4:6] = 0                               # nothing valid
+    src[0:2, 6:8] = [[0, 0], [0, 777]]             # single sample
+    dst = np.empty((2, 4), dtype=np.float32)
+    cnt = np.empty((2, 4), dtype=np.uint8)
+    oracle.lib().yo_pyrdown(C.byref(cfg), 8, 4, src.ctypes.data, dst.ctypes.data, cnt.ctypes.data)
+    assert list(cnt[0]) == [4, 2, 0, 1]
+    assert list(dst[0]) == [1015.0, 1005.0, 0.0, 777.0]
+    assert not dst[1].any() and not cnt[1].any()
+
+
+def test_identity_motion(oracle, pkg):
+    """same frame as current and previous: every valid pixel matches itself, residuals are
+    exactly zero, J^T r = 0, and the pose stays the identity."""
+    cfg = small_cfg(oracle)
+    raw = pkg.synth_sequence(1, 160, 120, sequence=1)[0]
+    f = oracle.OFrame(cfg, raw)
+    for level in range(3):
+        sums, corr = oracle.icp_sums(cfg, level, f, f, IDENT)
+        h, w = corr.shape
+        idx = np.arange(h * w).reshape(h, w)
+        both = f.mask(level) == 3
+        assert np.array_equal(corr[both], idx[both])
+        assert np.all(corr[~both] == -1)
+        assert sums[28] == both.sum()
+        assert not sums[21:28].any()
+    rel, status, inl = oracle.track_pair(cfg, f, f)
+    assert status == 0 and inl == (f.mask(0) == 3).sum()
+    assert np.array_equal(rel, IDENT.astype(np.float64))
+
+
+def test_known_motion_recovery(oracle, small_seq):
+    frames, gt = small_seq
+    cfg = oracle.default_config()
+    poses, status, _ = oracle.track_sequence(cfg, frames[:3])
+    assert list(status) == [1, 0, 0]
+    for i in range(3):
+        P, G = poses[i].astype(np.float64).reshape(3, 4), gt[i].reshape(3, 4)
+        assert np.linalg.norm(P[:, 3] - G[:, 3]) < 1e-3
+        assert np.linalg.norm(P[:, :3] - G[:, :3]) < 1e-3
+
+
+def test_reduction_matches_float64_sum(oracle, small_seq):
+    """the fixed-order float tree must agree with a plain float64 sum of the per-pixel terms."""
+    frames, gt = small_seq
+    cfg = oracle.default_config()
+    prev, cur = oracle.OFrame(cfg, frames[0]), oracle.OFrame(cfg, frames[1])
+    pose = gt[1].astype(np.float32)
+    sums, corr = oracle.icp_sums(cfg, 0, cur, prev, pose)
+    ok = corr >= 0
+    P = pose.reshape(3, 4)
+    vc = cur.vmap(0)[ok][:, :3]
+    # the transformed point in float32 with the oracle's operation order (residuals are ~1e-4 m on
+    # ~3 m coordinates, so float32 rounding of T*v is the dominant term and must be reproduced);
+    # everything after it in float64
+    vt = np.stack([((P[i, 0] * vc[:, 0] + P[i, 1] * vc[:, 1]) + P[i, 2] * vc[:, 2]) + P[i, 3] for i in range(3)],
+                  axis=1).astype(np.float64)
+    q = corr[ok]
+    vp = prev.vmap(0).reshape(-1, 4)[q][:, :3].astype(np.float64)
+    npv = prev.nmap(0).reshape(-1, 4)[q][:, :3].astype(np.float64)
+    r = np.einsum("ij,ij->i", npv, vp - vt)
+    J = np.concatenate([np.cross(vt, npv), npv], axis=1)
+    A, b = J.T @ J, J.T @ r
+    k = 0
+    for i in range(6):
+        for j in range(i, 6):
+            assert abs(sums[k] - A[i, j]) <= 2e-5 * max(1.0, abs(A[i, j]))
+            k += 1
+    assert np.allclose(sums[21:27], b, rtol=1e-3, atol=2e-4)
+    assert sums[28] == ok.sum()
+    for ppt in (1, 2, 8):  # a different tile geometry regroups the sum but not its value
+        cfg2 = oracle.default_config(icp_ppt=ppt)
+        s2, c2 = oracle.icp_sums(cfg2, 0, cur, prev, pose)
+        assert np.array_equal(c2, corr) and s2[28] == sums[28]
+        assert np.allclose(s2[:28], sums[:28], rtol=1e-4, atol=1e-4)
+
+
+def test_solve_update_against_numpy_scipy(oracle):
+    rng = np.random.default_rng(5)
+    cfg = oracle.default_config()
+    for trial in range(20):
+        J = rng.normal(size=(400, 6))
+        xi = rng.normal(size=6) * (0.02 if trial < 15 else 1.0)  # also large rotations for the exp series
+        r = J @ xi
+        A, b = J.T @ J, J.T @ r
+        sums = np.zeros(32)
+        k = 0
+        for i in range(6):
+            for j in range(i, 6):
+                sums[k] = A[i, j]
+                k += 1
+        sums[21:27] = b
+        sums[28] = 400
+        R0 = Rotation.from_rotvec(rng.normal(size=3) * 0.3).as_matrix()
+        t0 = rng.normal(size=3)
+        pose_d = np.concatenate([R0, t0[:, None]], axis=1).reshape(12).copy()
+        pose_f = np.zeros(12, dtype=np.float32)
+        assert oracle.lib().yo_solve_update(C.byref(cfg), sums.ctypes.data, pose_d.ctypes.data, pose_f.ctypes.data) == 1
+        x = np.linalg.solve(A, b)
+        w, u = x[:3], x[3:]
+        Rinc = Rotation.from_rotvec(w).as_matrix()
+        th = np.linalg.norm(w)
+        Wx = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+        V = np.eye(3) + (1 - np.cos(th)) / th**2 * Wx + (th - np.sin(th)) / th**3 * Wx @ Wx
+        want = np.concatenate([Rinc @ R0, (Rinc @ t0 + V @ u)[:, None]], axis=1).reshape(12)
+        assert np.allclose(pose_d, want, rtol=0, atol=1e-9)
+        assert np.array_equal(pose_f, pose_d.astype(np.float32))
+
+
+def test_solve_failure_policy(oracle):
+    cfg = oracle.default_config()
+    ident = IDENT.astype(np.float64).copy()
+    pf = IDENT.copy()
+    sums = np.zeros(32)
+    sums[28] = 10  # too few inliers
+    assert oracle.lib().yo_solve_update(C.byref(cfg), sums.ctypes.data, ident.ctypes.data, pf.ctypes.data) == 0
+    sums[28] = 1000  # enough inliers but a singular (all-zero) system
+    assert oracle.lib().yo_solve_update(C.byref(cfg), sums.ctypes.data, ident.ctypes.data, pf.ctypes.data) == 0
+    sums[0] = np.nan
+    assert oracle.lib().yo_solve_update(C.byref(cfg), sums.ctypes.data, ident.ctypes.data, pf.ctypes.data) == 0
+    assert np.array_equal(ident, IDENT.astype(np.float64))  # pose untouched, never NaN
+
+
+def test_empty_and_ragged_inputs(oracle):
+    cfg = small_cfg(oracle)
+    empty = np.zeros((3, 120, 160), dtype=np.uint16)
+    poses, status, _ = oracle.track_sequence(cfg, empty)
+    assert list(status) == [1, 2, 2] and all(np.array_equal(p, IDENT) for p in poses)
+    half = np.full((2, 120, 160), 1500, dtype=np.uint16)
+    half[:, :, 80:] = 0  # ragged validity: half the image
+    poses, status, _ = oracle.track_sequence(cfg, half)
+    assert status[1] in (0, 2) and np.isfinite(poses).all()
+
+
+def test_golden_fixture(oracle):
+    g = np.load(os.path.join(HERE, "golden", "golden_160x120.npz"))
+    frames = g["frames"]
+    cfg = small_cfg(oracle)
+    poses, status, _ = oracle.track_sequence(cfg, frames)
+    assert np.array_equal(poses.view(np.uint32), g["poses"].view(np.uint32))
+    assert np.array_equal(status, g["status"])
+    prev, cur = oracle.OFrame(cfg, frames[0]), oracle.OFrame(cfg, frames[1])
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()  # noqa: E731
+    for level in range(3):
+        sums, corr = oracle.icp_sums(cfg, level, cur, prev, IDENT)
+        assert np.array_equal(sums.view(np.uint64), g[f"sums_l{level}"].view(np.uint64))
+        assert np.array_equal(corr, g[f"corr_l{level}"])
+        assert np.array_equal(cur.mask(level), g[f"mask_l{level}"])
+        assert sha(cur.depth(level)) == str(g[f"depth_sha_l{level}"])
+        assert sha(cur.vmap(level)) == str(g[f"vmap_sha_l{level}"])
+        assert sha(cur.nmap(level)) == str(g[f"nmap_sha_l{level}"])
