@@ -19,9 +19,10 @@
  * youth_cuda_last_error() returns a thread-local description of the last failure.
  * There is no CPU fallback: without a CUDA device every compute entry point fails.
  *
- * Numerical contract (frozen by oracle/youth_oracle.c): no
- * fused multiply-add anywhere, IEEE division/sqrt, fixed-order reductions -- the
- * device results are bit-identical to the CPU oracle.
+ * Numerical contract (frozen by oracle/youth_oracle.c): fused
+ * multiply-add only where the specification names it (stage 3), never by compiler
+ * contraction; IEEE division/sqrt; fixed-order reductions -- the device results are
+ * bit-identical to the CPU oracle.
  */
 #ifndef YOUTH_CUDA_H
 #define YOUTH_CUDA_H
@@ -36,7 +37,13 @@ extern "C" {
 #define YOUTH_CUDA_ABI_VERSION 1
 #define YOUTH_MAX_LEVELS 4
 #define YOUTH_ICP_THREADS 256 /* threads per ICP tile (reduction geometry, part of the spec) */
-#define YOUTH_SUM_SLOTS 32    /* 21 JtJ + 6 Jtr + sum r^2 + inlier count + 3 spare */
+#define YOUTH_SUM_SLOTS 32    /* 21 JtJ + 6 Jtr + sum r^2 + inlier count + 3 duplicates */
+/* Layout of the 32 sums (youth_cuda_debug_icp): 16 pairs sized for one packed
+ * fma.rn.f32x2 each.  A[i][j] (i <= j) lives at: row 0 -> 0..5; row 1 -> 7..11; row 2 -> 12..15;
+ * row 3 -> 17..19; row 4 -> 20..21; row 5 -> 23; slots 6, 16, 22 duplicate A10, A32, A54. */
+#define YOUTH_SUMS_B0 24      /* J^T r: slots 24..29 */
+#define YOUTH_SUMS_RR 30      /* sum of r^2          */
+#define YOUTH_SUMS_COUNT 31   /* inlier count        */
 
 typedef struct youth_cuda_handle youth_cuda_handle;
 

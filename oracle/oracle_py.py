@@ -39,7 +39,7 @@ class Frame(C.Structure):
 
 
 def build(force=False):
-    so = os.path.join(HERE, "_build", "libyouth_oracle.so")
+    so = os.path.join(HERE, "_build", "libyouth_oracle_hwfma.so")
     src = os.path.join(HERE, "youth_oracle.c")
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
         subprocess.run(["make", "-C", HERE, "all"], check=True, capture_output=True)
@@ -65,11 +65,14 @@ def fast_supported():
 def lib(fast=False):
     if fast and not fast_supported():
         raise RuntimeError("host CPU lacks AVX2/FMA: speed build of the oracle not usable")
-    key = "fast" if fast else "parity"
+    # parity build: with hardware FMA when the host has it (fmaf() inlined), else the portable
+    # build that calls libm's fmaf() -- both are single-rounding, results are identical
+    key = "fast" if fast else ("hwfma" if fast_supported() else "parity")
     if key in _libs:
         return _libs[key]
     build()
-    path = os.path.join(HERE, "_build", "libyouth_oracle_fast.so" if fast else "libyouth_oracle.so")
+    name = {"fast": "libyouth_oracle_fast.so", "hwfma": "libyouth_oracle_hwfma.so", "parity": "libyouth_oracle.so"}[key]
+    path = os.path.join(HERE, "_build", name)
     L = C.CDLL(path)
     CP = C.POINTER(OracleConfig)
     FP = C.POINTER(Frame)

@@ -8,7 +8,7 @@
  *                                       conversion of reference SLAM.cpp:133-134,153-155)
  *   stage 2  yo_vertex_normal           back-projection per reference viewerModule.c:341-345
  *   stage 3  icp_pixel                  projective association + point-to-plane residual/Jacobian
- *   stage 4  yo_icp_sums                fixed-order 27(+2)-float reduction
+ *   stage 4  yo_icp_sums                fixed-order reduction of the 27 (+2, +3 duplicate) sums
  *   stage 5  yo_solve_update            6x6 solve + SE(3) update
  */
 #define _POSIX_C_SOURCE 200809L
@@ -247,23 +247,37 @@ void yo_preprocess(const yo_config* c, const uint16_t* raw, yo_frame* f) {
 
 /* ------------------------------------------------------------------ stage 3 */
 
+/* slot layout of the 32 sums: 16 pairs, pair p = X[PA[p]] * (X[PB[p]], X[PB[p]+1]) with
+ * X = (J0..J5, r, 1); chosen so that the device can form every pair with one packed
+ * fma.rn.f32x2.  Slots 6, 16, 22 duplicate A10, A32, A54 and are ignored by the solve. */
+static const int YO_PA[16] = {0, 0, 0, 1, 1, 1, 2, 2, 3, 3, 4, 5, 6, 6, 6, -1};
+static const int YO_PB[16] = {0, 2, 4, 0, 2, 4, 2, 4, 2, 4, 4, 4, 0, 2, 4, -1};
+/* slot of A[i][j], i <= j */
+static const int YO_SLOT_A[6][6] = {{0, 1, 2, 3, 4, 5},      {1, 7, 8, 9, 10, 11},    {2, 8, 12, 13, 14, 15},
+                                    {3, 9, 13, 17, 18, 19},  {4, 10, 14, 18, 20, 21}, {5, 11, 15, 19, 21, 23}};
+#define YO_SLOT_B0 24
+#define YO_SLOT_RR 30
+#define YO_SLOT_COUNT 31
+
 /* One pixel of the current frame.  Returns the matched previous-frame pixel index or a
- * negative reject code; on a match fills val[0..28]:
- *   0..20  upper triangle of J J^T, row-major ((0,0),(0,1)..(0,5),(1,1)..(5,5))
- *   21..26 J r          27  r*r          28  1.0
- * with J = [ (T v) x n' , n' ],  r = n' . (v' - T v). */
+ * negative reject code; on a match ADDS its 32 terms into acc[] with one fused
+ * multiply-add per slot: acc[k] = fma(a, b, acc[k]).
+ * J = [ (T v) x n' , n' ],  r = n' . (v' - T v).
+ * Every fmaf() below is a single-rounding IEEE fused multiply-add and is part of the
+ * specification (the device issues fma.rn.f32 / fma.rn.f32x2 at the same places);
+ * everything else is one rounding per written operation. */
 static int icp_pixel(const yo_level* g, float dist2_thr, float cos_thr, const float* vc4,
                      const float* nc4, const float* vprev, const float* nprev, const float* P,
-                     float* val) {
+                     float* acc) {
   if (vc4[3] == 0.0f || nc4[3] == 0.0f) return YO_REJ_CUR_INVALID;
   const float x = vc4[0], y = vc4[1], z = vc4[2];
-  const float tx = ((P[0] * x + P[1] * y) + P[2] * z) + P[3];
-  const float ty = ((P[4] * x + P[5] * y) + P[6] * z) + P[7];
-  const float tz = ((P[8] * x + P[9] * y) + P[10] * z) + P[11];
+  const float tx = fmaf(P[0], x, fmaf(P[1], y, fmaf(P[2], z, P[3])));
+  const float ty = fmaf(P[4], x, fmaf(P[5], y, fmaf(P[6], z, P[7])));
+  const float tz = fmaf(P[8], x, fmaf(P[9], y, fmaf(P[10], z, P[11])));
   if (!(tz > 0.0f)) return YO_REJ_BEHIND;
   const float iz = 1.0f / tz;
-  const float ur = ((tx * g->fx) * iz + g->cx) + 0.5f;
-  const float vr = ((ty * g->fy) * iz + g->cy) + 0.5f;
+  const float ur = fmaf(tx * g->fx, iz, g->cx + 0.5f);
+  const float vr = fmaf(ty * g->fy, iz, g->cy + 0.5f);
   if (!(ur >= 0.0f && ur < (float)g->w && vr >= 0.0f && vr < (float)g->h)) return YO_REJ_OUT_OF_IMAGE;
   const int ui = (int)ur, vi = (int)vr; /* nearest pixel: floor(u + 0.5) */
   const int q = vi * g->w + ui;
@@ -271,28 +285,29 @@ static int icp_pixel(const yo_level* g, float dist2_thr, float cos_thr, const fl
   const float* np = nprev + 4 * (size_t)q;
   if (vp[3] == 0.0f || np[3] == 0.0f) return YO_REJ_PREV_INVALID;
   const float dx = vp[0] - tx, dy = vp[1] - ty, dz = vp[2] - tz;
-  const float dist2 = (dx * dx + dy * dy) + dz * dz;
+  const float dist2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
   if (!(dist2 <= dist2_thr)) return YO_REJ_DISTANCE;
   const float nx = nc4[0], ny = nc4[1], nz = nc4[2];
-  const float rnx = (P[0] * nx + P[1] * ny) + P[2] * nz;
-  const float rny = (P[4] * nx + P[5] * ny) + P[6] * nz;
-  const float rnz = (P[8] * nx + P[9] * ny) + P[10] * nz;
-  const float cosang = (rnx * np[0] + rny * np[1]) + rnz * np[2];
+  const float rnx = fmaf(P[2], nz, fmaf(P[1], ny, P[0] * nx));
+  const float rny = fmaf(P[6], nz, fmaf(P[5], ny, P[4] * nx));
+  const float rnz = fmaf(P[10], nz, fmaf(P[9], ny, P[8] * nx));
+  const float cosang = fmaf(rnz, np[2], fmaf(rny, np[1], rnx * np[0]));
   if (!(cosang >= cos_thr)) return YO_REJ_ANGLE;
-  const float r = (np[0] * dx + np[1] * dy) + np[2] * dz;
-  float J[6];
-  J[0] = ty * np[2] - tz * np[1];
-  J[1] = tz * np[0] - tx * np[2];
-  J[2] = tx * np[1] - ty * np[0];
-  J[3] = np[0];
-  J[4] = np[1];
-  J[5] = np[2];
-  int k = 0;
-  for (int i = 0; i < 6; ++i)
-    for (int j = i; j < 6; ++j) val[k++] = J[i] * J[j];
-  for (int i = 0; i < 6; ++i) val[k++] = J[i] * r;
-  val[k++] = r * r;
-  val[k++] = 1.0f;
+  float X[8];
+  X[6] = fmaf(np[2], dz, fmaf(np[1], dy, np[0] * dx)); /* r */
+  X[0] = fmaf(ty, np[2], -(tz * np[1]));
+  X[1] = fmaf(tz, np[0], -(tx * np[2]));
+  X[2] = fmaf(tx, np[1], -(ty * np[0]));
+  X[3] = np[0];
+  X[4] = np[1];
+  X[5] = np[2];
+  X[7] = 1.0f;
+  for (int p = 0; p < 15; ++p) {
+    acc[2 * p] = fmaf(X[YO_PA[p]], X[YO_PB[p]], acc[2 * p]);
+    acc[2 * p + 1] = fmaf(X[YO_PA[p]], X[YO_PB[p] + 1], acc[2 * p + 1]);
+  }
+  acc[30] = fmaf(X[6], X[6], acc[30]);
+  acc[31] = fmaf(X[7], X[7], acc[31]);
   return q;
 }
 
@@ -301,7 +316,8 @@ static int icp_pixel(const yo_level* g, float dist2_thr, float cos_thr, const fl
 /* Fixed-order reduction (identical tree on the device):
  *   tile   = YO_ICP_THREADS*ppt consecutive pixels (row-major linear index);
  *   thread t of a tile adds its pixels tile*T + j*256 + t, j = 0..ppt-1, in that order,
- *            into 29 float accumulators that start at +0 (rejected pixels add nothing);
+ *            into 32 float accumulators that start at +0, one fused multiply-add per slot
+ *            (rejected pixels add nothing);
  *   warp   : 32 lanes combined by the pairwise tree with strides 16, 8, 4, 2, 1;
  *   tile   : warp sums added in warp order, starting from warp 0's value (float);
  *   frame  : tile partials accumulated in double: chain w (0..7) adds tiles w, w+8, ...
@@ -327,12 +343,9 @@ void yo_icp_sums(const yo_config* c, int level, const yo_frame* cur, const yo_fr
       for (int t = 0; t < YO_ICP_THREADS; ++t) {
         const int p = tile * T + j * YO_ICP_THREADS + t;
         if (p >= npix) continue;
-        float val[YO_SUM_SLOTS];
         const int q = icp_pixel(&g, dist2_thr, c->cos_thresh, vc + 4 * (size_t)p, nc + 4 * (size_t)p, vp,
-                                np, pose, val);
+                                np, pose, acc[t]);
         if (corr) corr[p] = q;
-        if (q < 0) continue;
-        for (int k = 0; k < 29; ++k) acc[t][k] = acc[t][k] + val[k];
       }
     }
     float wsum[YO_ICP_THREADS / 32][YO_SUM_SLOTS];
@@ -418,16 +431,11 @@ static void mat3_mul(const double* a, const double* b, double* o) { /* 3x3 row-m
 }
 
 int yo_solve_update(const yo_config* c, const double* sums, double pose_d[12], float pose_f[12]) {
-  if (!(sums[28] >= (double)c->min_inliers)) return 0;
+  if (!(sums[YO_SLOT_COUNT] >= (double)c->min_inliers)) return 0;
   double A[6][6], b[6], L[6][6], yv[6], x[6];
-  int k = 0;
   for (int i = 0; i < 6; ++i)
-    for (int j = i; j < 6; ++j) {
-      A[i][j] = sums[k];
-      A[j][i] = sums[k];
-      ++k;
-    }
-  for (int i = 0; i < 6; ++i) b[i] = sums[21 + i];
+    for (int j = 0; j < 6; ++j) A[i][j] = sums[YO_SLOT_A[i][j]];
+  for (int i = 0; i < 6; ++i) b[i] = sums[YO_SLOT_B0 + i];
   double scale = A[0][0];
   for (int i = 1; i < 6; ++i)
     if (A[i][i] > scale) scale = A[i][i];
@@ -509,7 +517,7 @@ uint32_t yo_track_pair(const yo_config* c, const yo_frame* cur, const yo_frame* 
   for (int level = c->levels - 1; level >= 0; --level) {
     for (int it = 0; it < c->iters[level]; ++it) {
       yo_icp_sums(c, level, cur, prev, pf, sums, NULL);
-      inl = (int32_t)sums[28];
+      inl = (int32_t)sums[YO_SLOT_COUNT];
       if (!yo_solve_update(c, sums, rel, pf)) status |= YO_STATUS_LOST;
     }
   }

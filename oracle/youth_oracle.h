@@ -19,9 +19,11 @@
  *
  * Arithmetic rules (the device path obeys the same ones, which is what makes the
  * comparison bit-exact): float unless stated, one rounding per written operation
- * (compile with -ffp-contract=off), IEEE division and sqrt, no libm in anything that
- * depends on the data (tables of exp() are built once from the config), reductions in
- * the fixed order documented at yo_icp_sums().
+ * (compile with -ffp-contract=off) EXCEPT where the source says fmaf(), which is a
+ * single-rounding IEEE fused multiply-add on both sides (stage 3 only); IEEE division
+ * and sqrt; no libm in anything that depends on the data (tables of exp() are built once
+ * from the config; fmaf is exact by definition); reductions in the fixed order documented
+ * at yo_icp_sums().
  */
 #ifndef YOUTH_ORACLE_H
 #define YOUTH_ORACLE_H
@@ -35,6 +37,10 @@ extern "C" {
 #define YO_MAX_LEVELS 4
 #define YO_ICP_THREADS 256
 #define YO_SUM_SLOTS 32
+/* slot layout of the sums (see icp_pixel in youth_oracle.c) */
+#define YO_SUMS_B0 24
+#define YO_SUMS_RR 30
+#define YO_SUMS_COUNT 31
 #define YO_BILATERAL_RADIUS 3
 #define YO_RANGE_LUT_MAX 1024
 

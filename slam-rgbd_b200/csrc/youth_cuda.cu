@@ -255,7 +255,7 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
         cx = (cx - 0.5f) * 0.5f;
         cy = (cy - 0.5f) * 0.5f;
       }
-      h->lv[l] = LevelGeom{w, hh, fx, fy, cx, cy};
+      h->lv[l] = LevelGeom{w, hh, fx, fy, cx, cy, cx + 0.5f, cy + 0.5f};
       h->npix[l] = w * hh;
     }
   }

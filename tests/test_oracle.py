@@ -12,6 +12,9 @@ from scipy.spatial.transform import Rotation
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 IDENT = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], dtype=np.float32)
+# slot of A[i][j] (i <= j) in the 32 sums: pairs sized for fma.rn.f32x2 (include/youth_cuda.h)
+SLOT_A = [[0, 1, 2, 3, 4, 5], [1, 7, 8, 9, 10, 11], [2, 8, 12, 13, 14, 15], [3, 9, 13, 17, 18, 19],
+          [4, 10, 14, 18, 20, 21], [5, 11, 15, 19, 21, 23]]
 
 
 def small_cfg(O, w=160, h=120, **kw):
@@ -122,8 +125,8 @@ def test_identity_motion(oracle, pkg):
         both = f.mask(level) == 3
         assert np.array_equal(corr[both], idx[both])
         assert np.all(corr[~both] == -1)
-        assert sums[28] == both.sum()
-        assert not sums[21:28].any()
+        assert sums[31] == both.sum()
+        assert not sums[24:31].any()
     rel, status, inl = oracle.track_pair(cfg, f, f)
     assert status == 0 and inl == (f.mask(0) == 3).sum()
     assert np.array_equal(rel, IDENT.astype(np.float64))
@@ -150,29 +153,34 @@ def test_reduction_matches_float64_sum(oracle, small_seq):
     ok = corr >= 0
     P = pose.reshape(3, 4)
     vc = cur.vmap(0)[ok][:, :3]
-    # the transformed point in float32 with the oracle's operation order (residuals are ~1e-4 m on
+    # the transformed point in float32 with the oracle's operation order (nested fused multiply-adds) (residuals are ~1e-4 m on
     # ~3 m coordinates, so float32 rounding of T*v is the dominant term and must be reproduced);
     # everything after it in float64
-    vt = np.stack([((P[i, 0] * vc[:, 0] + P[i, 1] * vc[:, 1]) + P[i, 2] * vc[:, 2]) + P[i, 3] for i in range(3)],
-                  axis=1).astype(np.float64)
+    def fma32(a, b, c):  # float32 fused multiply-add: the float64 product of two floats is exact
+        return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+    vt = np.stack([fma32(np.full_like(vc[:, 0], P[i, 0]), vc[:, 0],
+                         fma32(np.full_like(vc[:, 0], P[i, 1]), vc[:, 1],
+                               fma32(np.full_like(vc[:, 0], P[i, 2]), vc[:, 2], np.full_like(vc[:, 0], P[i, 3]))))
+                   for i in range(3)], axis=1).astype(np.float64)
     q = corr[ok]
     vp = prev.vmap(0).reshape(-1, 4)[q][:, :3].astype(np.float64)
     npv = prev.nmap(0).reshape(-1, 4)[q][:, :3].astype(np.float64)
     r = np.einsum("ij,ij->i", npv, vp - vt)
     J = np.concatenate([np.cross(vt, npv), npv], axis=1)
     A, b = J.T @ J, J.T @ r
-    k = 0
     for i in range(6):
         for j in range(i, 6):
-            assert abs(sums[k] - A[i, j]) <= 2e-5 * max(1.0, abs(A[i, j]))
-            k += 1
-    assert np.allclose(sums[21:27], b, rtol=1e-3, atol=2e-4)
-    assert sums[28] == ok.sum()
+            assert abs(sums[SLOT_A[i][j]] - A[i, j]) <= 2e-5 * max(1.0, abs(A[i, j]))
+    assert np.allclose(sums[24:30], b, rtol=1e-3, atol=2e-4)
+    assert sums[31] == ok.sum()
+    for dup, twin in ((6, 1), (16, 13), (22, 21)):  # duplicate slots carry the same sums
+        assert sums[dup] == sums[twin]
     for ppt in (1, 2, 8):  # a different tile geometry regroups the sum but not its value
         cfg2 = oracle.default_config(icp_ppt=ppt)
         s2, c2 = oracle.icp_sums(cfg2, 0, cur, prev, pose)
-        assert np.array_equal(c2, corr) and s2[28] == sums[28]
-        assert np.allclose(s2[:28], sums[:28], rtol=1e-4, atol=1e-4)
+        assert np.array_equal(c2, corr) and s2[31] == sums[31]
+        assert np.allclose(s2[:31], sums[:31], rtol=1e-4, atol=1e-4)
 
 
 def test_solve_update_against_numpy_scipy(oracle):
@@ -184,13 +192,11 @@ def test_solve_update_against_numpy_scipy(oracle):
         r = J @ xi
         A, b = J.T @ J, J.T @ r
         sums = np.zeros(32)
-        k = 0
         for i in range(6):
             for j in range(i, 6):
-                sums[k] = A[i, j]
-                k += 1
-        sums[21:27] = b
-        sums[28] = 400
+                sums[SLOT_A[i][j]] = A[i, j]
+        sums[24:30] = b
+        sums[31] = 400
         R0 = Rotation.from_rotvec(rng.normal(size=3) * 0.3).as_matrix()
         t0 = rng.normal(size=3)
         pose_d = np.concatenate([R0, t0[:, None]], axis=1).reshape(12).copy()
@@ -212,9 +218,9 @@ def test_solve_failure_policy(oracle):
     ident = IDENT.astype(np.float64).copy()
     pf = IDENT.copy()
     sums = np.zeros(32)
-    sums[28] = 10  # too few inliers
+    sums[31] = 10  # too few inliers
     assert oracle.lib().yo_solve_update(C.byref(cfg), sums.ctypes.data, ident.ctypes.data, pf.ctypes.data) == 0
-    sums[28] = 1000  # enough inliers but a singular (all-zero) system
+    sums[31] = 1000  # enough inliers but a singular (all-zero) system
     assert oracle.lib().yo_solve_update(C.byref(cfg), sums.ctypes.data, ident.ctypes.data, pf.ctypes.data) == 0
     sums[0] = np.nan
     assert oracle.lib().yo_solve_update(C.byref(cfg), sums.ctypes.data, ident.ctypes.data, pf.ctypes.data) == 0
