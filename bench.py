@@ -237,8 +237,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     stream = torch.cuda.Stream()
+    extra = {"icp_ppt": args.ppt} if args.ppt else {}
     cfg = pkg.default_config(batch=args.batch, n_streams=1, device=local, traj_capacity=FRAMES,
-                             stream=stream.cuda_stream)
+                             stream=stream.cuda_stream, **extra)
     trk = B.Tracker(cfg)
 
     # one independent sequence per rank (seed 20261018 + rank)
@@ -409,7 +410,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="frames per launch group")
+    ap.add_argument("--batch", type=int, default=32, help="frames per launch group")
+    ap.add_argument("--ppt", type=int, default=0, help="override icp_ppt (reduction geometry; 0 = library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

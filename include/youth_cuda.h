@@ -36,7 +36,7 @@ extern "C" {
 
 #define YOUTH_CUDA_ABI_VERSION 1
 #define YOUTH_MAX_LEVELS 4
-#define YOUTH_ICP_THREADS 256 /* threads per ICP tile (reduction geometry, part of the spec) */
+#define YOUTH_ICP_LANES 32    /* lanes per ICP run (reduction geometry, part of the spec) */
 #define YOUTH_SUM_SLOTS 32    /* 21 JtJ + 6 Jtr + sum r^2 + inlier count + 3 duplicates */
 /* Layout of the 32 sums (youth_cuda_debug_icp): 16 pairs sized for one packed
  * fma.rn.f32x2 each.  A[i][j] (i <= j) lives at: row 0 -> 0..5; row 1 -> 7..11; row 2 -> 12..15;
@@ -61,7 +61,8 @@ typedef struct youth_cuda_config {
   float dist_thresh_m;    /* correspondence rejection: |T v - v'| > dist_thresh               */
   float cos_thresh;       /* correspondence rejection: (R n) . n' < cos_thresh                */
   int32_t min_inliers;    /* an iteration with fewer inliers leaves the pose unchanged        */
-  int32_t icp_ppt;        /* pixels per thread per ICP tile: 1, 2, 4 or 8 (tile = 256*ppt px) */
+  int32_t icp_ppt;        /* pixels per lane per ICP run at level 0 (power of two, 1..256); a run is
+                             32*ppt pixels (strided sweep) reduced by one warp; level l uses max(1, ppt >> 2l) */
   int32_t n_streams;      /* independent sequences tracked by this handle (>= 1)              */
   int32_t batch;          /* max frames per sequence per youth_cuda_track_batch call (>= 1)   */
   int32_t traj_capacity;  /* max poses kept per sequence                                      */

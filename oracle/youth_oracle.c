@@ -43,7 +43,7 @@ void yo_default_config(yo_config* c) {
   c->dist_thresh_m = 0.10f;
   c->cos_thresh = 0.93969262f; /* cos(20 deg) */
   c->min_inliers = 100;
-  c->icp_ppt = 4;
+  c->icp_ppt = 64;
 }
 
 int yo_level_geometry(const yo_config* c, int level, yo_level* g) {
@@ -314,68 +314,65 @@ static int icp_pixel(const yo_level* g, float dist2_thr, float cos_thr, const fl
 /* ------------------------------------------------------------------ stage 4 */
 
 /* Fixed-order reduction (identical tree on the device):
- *   tile   = YO_ICP_THREADS*ppt consecutive pixels (row-major linear index);
- *   thread t of a tile adds its pixels tile*T + j*256 + t, j = 0..ppt-1, in that order,
- *            into 32 float accumulators that start at +0, one fused multiply-add per slot
- *            (rejected pixels add nothing);
- *   warp   : 32 lanes combined by the pairwise tree with strides 16, 8, 4, 2, 1;
- *   tile   : warp sums added in warp order, starting from warp 0's value (float);
- *   frame  : tile partials accumulated in double: chain w (0..7) adds tiles w, w+8, ...
+ *   nruns  = ceil(npix / (32*ppr)) runs per frame, ppr = max(1, icp_ppt >> 2*level);
+ *   lane l of run k adds the pixels (row-major linear index) j*(32*nruns) + 32*k + l,
+ *            j = 0..ppr-1, in that order (all runs sweep the image together), into 32
+ *            float accumulators that start at +0, one fused multiply-add per slot (rejected
+ *            pixels add nothing);
+ *   run    : the 32 lanes are combined by the pairwise tree with strides 16, 8, 4, 2, 1;
+ *   frame  : run partials accumulated in double: chain w (0..7) adds runs w, w+8, ...
  *            starting from 0.0, then the 8 chains are added in order starting from chain 0. */
+static int run_ppr(const yo_config* c, int level) {
+  int ppr = c->icp_ppt >> (2 * level);
+  return ppr < 1 ? 1 : ppr;
+}
+
 void yo_icp_sums(const yo_config* c, int level, const yo_frame* cur, const yo_frame* prev,
                  const float pose[12], double* sums, int32_t* corr) {
   yo_level g;
   yo_level_geometry(c, level, &g);
   const int npix = g.w * g.h;
-  const int T = YO_ICP_THREADS * c->icp_ppt;
-  const int ntiles = (npix + T - 1) / T;
+  const int ppr = run_ppr(c, level);
+  const int T = YO_ICP_LANES * ppr;
+  const int nruns = (npix + T - 1) / T;
   const float dist2_thr = c->dist_thresh_m * c->dist_thresh_m;
   const float* vc = cur->vmap[level];
   const float* nc = cur->nmap[level];
   const float* vp = prev->vmap[level];
   const float* np = prev->nmap[level];
 
-  float(*acc)[YO_SUM_SLOTS] = (float(*)[YO_SUM_SLOTS])malloc(sizeof(float) * YO_SUM_SLOTS * YO_ICP_THREADS);
-  float* partial = (float*)malloc(sizeof(float) * YO_SUM_SLOTS * (size_t)ntiles);
-  for (int tile = 0; tile < ntiles; ++tile) {
-    memset(acc, 0, sizeof(float) * YO_SUM_SLOTS * YO_ICP_THREADS);
-    for (int j = 0; j < c->icp_ppt; ++j) {
-      for (int t = 0; t < YO_ICP_THREADS; ++t) {
-        const int p = tile * T + j * YO_ICP_THREADS + t;
+  float* partial = (float*)malloc(sizeof(float) * YO_SUM_SLOTS * (size_t)nruns);
+  for (int run = 0; run < nruns; ++run) {
+    float acc[YO_ICP_LANES][YO_SUM_SLOTS];
+    memset(acc, 0, sizeof(acc));
+    for (int j = 0; j < ppr; ++j) {
+      for (int l = 0; l < YO_ICP_LANES; ++l) {
+        const int p = j * (YO_ICP_LANES * nruns) + YO_ICP_LANES * run + l;
         if (p >= npix) continue;
         const int q = icp_pixel(&g, dist2_thr, c->cos_thresh, vc + 4 * (size_t)p, nc + 4 * (size_t)p, vp,
-                                np, pose, acc[t]);
+                                np, pose, acc[l]);
         if (corr) corr[p] = q;
       }
     }
-    float wsum[YO_ICP_THREADS / 32][YO_SUM_SLOTS];
-    for (int w = 0; w < YO_ICP_THREADS / 32; ++w) {
-      for (int k = 0; k < YO_SUM_SLOTS; ++k) {
-        float v[32];
-        for (int l = 0; l < 32; ++l) v[l] = acc[w * 32 + l][k];
-        for (int s = 16; s >= 1; s >>= 1)
-          for (int l = 0; l < s; ++l) v[l] = v[l] + v[l + s];
-        wsum[w][k] = v[0];
-      }
-    }
     for (int k = 0; k < YO_SUM_SLOTS; ++k) {
-      float s = wsum[0][k];
-      for (int w = 1; w < YO_ICP_THREADS / 32; ++w) s = s + wsum[w][k];
-      partial[(size_t)tile * YO_SUM_SLOTS + k] = s;
+      float v[YO_ICP_LANES];
+      for (int l = 0; l < YO_ICP_LANES; ++l) v[l] = acc[l][k];
+      for (int s = 16; s >= 1; s >>= 1)
+        for (int l = 0; l < s; ++l) v[l] = v[l] + v[l + s];
+      partial[(size_t)run * YO_SUM_SLOTS + k] = v[0];
     }
   }
   for (int k = 0; k < YO_SUM_SLOTS; ++k) {
     double chain[8];
     for (int w = 0; w < 8; ++w) {
       double d = 0.0;
-      for (int tile = w; tile < ntiles; tile += 8) d = d + (double)partial[(size_t)tile * YO_SUM_SLOTS + k];
+      for (int run = w; run < nruns; run += 8) d = d + (double)partial[(size_t)run * YO_SUM_SLOTS + k];
       chain[w] = d;
     }
     double tot = chain[0];
     for (int w = 1; w < 8; ++w) tot = tot + chain[w];
     sums[k] = tot;
   }
-  free(acc);
   free(partial);
 }
 

@@ -35,7 +35,7 @@ extern "C" {
 #endif
 
 #define YO_MAX_LEVELS 4
-#define YO_ICP_THREADS 256
+#define YO_ICP_LANES 32
 #define YO_SUM_SLOTS 32
 /* slot layout of the sums (see icp_pixel in youth_oracle.c) */
 #define YO_SUMS_B0 24

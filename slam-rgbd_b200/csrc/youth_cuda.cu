@@ -7,8 +7,8 @@
  *   ring      per stream R = batch+1 slots; per slot and pyramid level: float depth,
  *             float4 vertex map, float4 normal map, uint8 pyramid count
  *   raw       2 x [S][batch] uint16 frames (double-buffered H2D landing zone)
- *   pairs     per (stream, frame-in-group): double+float relative pose, per-tile partial
- *             sums [max_tiles][32] float, reduced sums [32] double, status
+ *   pairs     per (stream, frame-in-group): double+float relative pose, per-run partial
+ *             sums [max_runs][32] float, reduced sums [32] double, status
  *   sequence  per stream: frame count, world pose (double), trajectory [cap][12] float,
  *             status [cap], last inlier count
  */
@@ -50,9 +50,9 @@ struct youth_cuda_handle {
   int S, B, R, P; /* streams, batch, ring slots, max pairs */
   LevelGeom lv[YOUTH_MAX_LEVELS];
   int npix[YOUTH_MAX_LEVELS];
-  int ntiles[YOUTH_MAX_LEVELS];
-  int max_tiles;
-  int tile_px;
+  int ppr[YOUTH_MAX_LEVELS];   /* pixels per lane per run */
+  int nruns[YOUTH_MAX_LEVELS]; /* runs per frame pair */
+  int max_runs;
   cudaStream_t stream, copy_stream;
   bool own_stream;
   /* ring */
@@ -150,7 +150,7 @@ extern "C" int youth_cuda_default_config(youth_cuda_config* c) {
   c->dist_thresh_m = 0.10f;
   c->cos_thresh = 0.93969262f;
   c->min_inliers = 100;
-  c->icp_ppt = 4;
+  c->icp_ppt = 64;
   c->n_streams = 1;
   c->batch = 8;
   c->traj_capacity = 4096;
@@ -168,7 +168,7 @@ static int validate(const youth_cuda_config* c) {
   if (!(c->fx > 0.f) || !(c->fy > 0.f) || !(c->depth_factor > 0.f)) return fail("bad intrinsics / depth factor");
   if (c->depth_min_mm < 1 || c->depth_max_mm > 65535 || c->depth_min_mm > c->depth_max_mm)
     return fail("depth range must satisfy 1 <= min <= max <= 65535");
-  if (c->icp_ppt != 1 && c->icp_ppt != 2 && c->icp_ppt != 4 && c->icp_ppt != 8) return fail("icp_ppt must be 1, 2, 4 or 8");
+  if (c->icp_ppt < 1 || c->icp_ppt > 256 || (c->icp_ppt & (c->icp_ppt - 1))) return fail("icp_ppt must be a power of two in 1..256");
   if (c->n_streams < 1 || c->n_streams > YK_MAX_STREAMS) return fail("n_streams must be 1..%d", YK_MAX_STREAMS);
   if (c->batch < 1 || c->batch > 1024) return fail("batch must be 1..1024");
   if (c->traj_capacity < 1) return fail("traj_capacity must be >= 1");
@@ -259,11 +259,15 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
       h->npix[l] = w * hh;
     }
   }
-  h->tile_px = YOUTH_ICP_THREADS * cfg->icp_ppt;
-  h->max_tiles = 0;
+  h->max_runs = 0;
   for (int l = 0; l < cfg->levels; ++l) {
-    h->ntiles[l] = (h->npix[l] + h->tile_px - 1) / h->tile_px;
-    if (h->ntiles[l] > h->max_tiles) h->max_tiles = h->ntiles[l];
+    /* reduction geometry (part of the spec): a run is 32 * ppr consecutive pixels, ppr shrinks
+     * 4x per level so that every level has about the same number of runs */
+    int ppr = cfg->icp_ppt >> (2 * l);
+    if (ppr < 1) ppr = 1;
+    h->ppr[l] = ppr;
+    h->nruns[l] = (h->npix[l] + 32 * ppr - 1) / (32 * ppr);
+    if (h->nruns[l] > h->max_runs) h->max_runs = h->nruns[l];
   }
   if (cfg->stream) {
     h->stream = (cudaStream_t)cfg->stream;
@@ -305,7 +309,7 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
   }
   CU(dalloc(&h->pose_d, (size_t)h->P * 12));
   CU(dalloc(&h->pose_f, (size_t)h->P * 12));
-  CU(dalloc(&h->partials, (size_t)h->P * h->max_tiles * 32));
+  CU(dalloc(&h->partials, (size_t)h->P * h->max_runs * 32));
   CU(dalloc(&h->sums, (size_t)h->P * 32));
   CU(dalloc(&h->pair_status, (size_t)h->P));
   CU(dalloc(&h->tickets, (size_t)h->P));
@@ -353,14 +357,10 @@ static RingGeom ring_of(const youth_cuda_handle* h, int n) {
 }
 
 template <bool DEBUG>
-static void launch_icp(youth_cuda_handle* h, const IcpParams& ip, dim3 grid, int level) {
+static void launch_icp(youth_cuda_handle* h, const IcpParams& ip, int pairs, int level) {
   ProfScope ps(h, YOUTH_PROF_ICP0 + level);
-  switch (h->cfg.icp_ppt) {
-    case 1: k_icp<1, DEBUG><<<grid, YOUTH_ICP_THREADS, 0, h->stream>>>(ip); break;
-    case 2: k_icp<2, DEBUG><<<grid, YOUTH_ICP_THREADS, 0, h->stream>>>(ip); break;
-    case 4: k_icp<4, DEBUG><<<grid, YOUTH_ICP_THREADS, 0, h->stream>>>(ip); break;
-    default: k_icp<8, DEBUG><<<grid, YOUTH_ICP_THREADS, 0, h->stream>>>(ip); break;
-  }
+  const dim3 grid((h->nruns[level] + YK_ICP_WARPS - 1) / YK_ICP_WARPS, pairs);
+  k_icp<DEBUG><<<grid, 32 * YK_ICP_WARPS, 0, h->stream>>>(ip);
 }
 
 static IcpParams icp_params(const youth_cuda_handle* h, int level, const RingGeom& ring) {
@@ -371,8 +371,9 @@ static IcpParams icp_params(const youth_cuda_handle* h, int level, const RingGeo
   ip.g = h->lv[level];
   ip.ring = ring;
   ip.npix = h->npix[level];
-  ip.ntiles = h->ntiles[level];
-  ip.max_tiles = h->max_tiles;
+  ip.ppr = h->ppr[level];
+  ip.nruns = h->nruns[level];
+  ip.max_runs = h->max_runs;
   ip.dist2_thr = h->cfg.dist_thresh_m * h->cfg.dist_thresh_m;
   ip.cos_thr = h->cfg.cos_thresh;
   ip.pose_f = h->pose_f;
@@ -447,7 +448,7 @@ static int enqueue_group(youth_cuda_handle* h, const uint16_t* const* raw_dev, i
   /* stages 3-5: coarse to fine, fixed iteration schedule, one launch per iteration, no host sync */
   for (int level = c.levels - 1; level >= 0; --level) {
     const IcpParams ip = icp_params(h, level, ring);
-    for (int it = 0; it < c.iters[level]; ++it) launch_icp<false>(h, ip, dim3(h->ntiles[level], frames), level);
+    for (int it = 0; it < c.iters[level]; ++it) launch_icp<false>(h, ip, frames, level);
   }
   /* pose chain + trajectory append */
   {
@@ -690,7 +691,7 @@ extern "C" int youth_cuda_debug_icp(youth_cuda_handle* h, int stream, int frame,
   ip.dbg_prev_slot = prev;
   ip.dbg_stream = stream;
   ip.do_solve = 0;
-  launch_icp<true>(h, ip, dim3(h->ntiles[level], 1), level);
+  launch_icp<true>(h, ip, 1, level);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(sums_out, h->sums, sizeof(double) * 32, cudaMemcpyDeviceToHost, h->stream));
   if (corr_out)

@@ -59,7 +59,7 @@ def test_config_struct_mirrors_header(pkg):
     assert C.sizeof(YouthConfig) == 112  # 26 x 4-byte fields + pointer, 8-byte aligned
     assert (cfg.width, cfg.height, cfg.levels, list(cfg.iters)[:3]) == (640, 480, 3, [10, 5, 4])
     assert np.float32(cfg.fx) == np.float32(570.3) and cfg.cx == 320.0 and cfg.cy == 240.0
-    assert cfg.depth_factor == 1000.0 and cfg.bilateral == 1 and cfg.icp_ppt == 4
+    assert cfg.depth_factor == 1000.0 and cfg.bilateral == 1 and cfg.icp_ppt == 64
 
 
 def test_oracle_and_product_defaults_agree(pkg, oracle):

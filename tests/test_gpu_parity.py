@@ -77,7 +77,7 @@ def test_preprocess_bit_exact(pkg, oracle, small_seq):
     trk.close()
 
 
-@pytest.mark.parametrize("ppt", [1, 2, 4, 8])
+@pytest.mark.parametrize("ppt", [1, 16, 64, 256])
 def test_icp_sums_and_correspondences(pkg, oracle, small_seq, ppt):
     """stage 3+4: correspondence indices (and reject codes) bit-exact; 29 sums bit-exact."""
     frames, gt = small_seq

@@ -19,7 +19,7 @@ def main():
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--levels", type=int, default=3)
-    ap.add_argument("--ppt", type=int, default=4)
+    ap.add_argument("--ppt", type=int, default=64)
     args = ap.parse_args()
     import torch
 
