@@ -5,7 +5,7 @@
  *
  * Device-resident state per handle (all in HBM, sized at init, nothing allocated per frame):
  *   ring      per stream R = batch+1 slots; per slot and pyramid level: float depth,
- *             float4 vertex map, float4 normal map, uint8 pyramid count
+ *             six float planes vx vy vz nx ny nz (24 B/pixel), uint8 pyramid count
  *   raw       2 x [S][batch] uint16 frames (double-buffered H2D landing zone)
  *   pairs     per (stream, frame-in-group): double+float relative pose, per-run partial
  *             sums [max_runs][32] float, reduced sums [32] double, status
@@ -57,8 +57,7 @@ struct youth_cuda_handle {
   bool own_stream;
   /* ring */
   float* depth[YOUTH_MAX_LEVELS];
-  float4* vmap[YOUTH_MAX_LEVELS];
-  float4* nmap[YOUTH_MAX_LEVELS];
+  float* maps[YOUTH_MAX_LEVELS]; /* [S][R][6][npix]: vx vy vz nx ny nz planes */
   uint8_t* pyrcnt[YOUTH_MAX_LEVELS];
   /* raw landing zone */
   uint16_t* raw[2];
@@ -192,8 +191,7 @@ extern "C" void youth_cuda_destroy(youth_cuda_handle* h) {
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   for (int l = 0; l < YOUTH_MAX_LEVELS; ++l) {
     cudaFree(h->depth[l]);
-    cudaFree(h->vmap[l]);
-    cudaFree(h->nmap[l]);
+    cudaFree(h->maps[l]);
     cudaFree(h->pyrcnt[l]);
   }
   for (int k = 0; k < 2; ++k) {
@@ -280,8 +278,7 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
   const size_t slots = (size_t)h->S * h->R;
   for (int l = 0; l < cfg->levels; ++l) {
     CU(dalloc(&h->depth[l], slots * h->npix[l]));
-    CU(dalloc(&h->vmap[l], slots * h->npix[l]));
-    CU(dalloc(&h->nmap[l], slots * h->npix[l]));
+    CU(dalloc(&h->maps[l], slots * 6 * h->npix[l]));
     CU(dalloc(&h->pyrcnt[l], slots * h->npix[l]));
   }
   const size_t frame_px = (size_t)cfg->width * cfg->height;
@@ -366,8 +363,7 @@ static void launch_icp(youth_cuda_handle* h, const IcpParams& ip, int pairs, int
 static IcpParams icp_params(const youth_cuda_handle* h, int level, const RingGeom& ring) {
   IcpParams ip;
   memset(&ip, 0, sizeof(ip));
-  ip.vmap = h->vmap[level];
-  ip.nmap = h->nmap[level];
+  ip.maps = h->maps[level];
   ip.g = h->lv[level];
   ip.ring = ring;
   ip.npix = h->npix[level];
@@ -405,7 +401,7 @@ static int enqueue_group(youth_cuda_handle* h, const uint16_t* const* raw_dev, i
     for (int s = 0; s < h->S; ++s) ip.raw[s] = raw_dev[s];
     for (int l = 0; l < c.levels; ++l) {
       ip.depth[l] = h->depth[l];
-      ip.vmap[l] = h->vmap[l];
+      ip.maps[l] = h->maps[l];
       ip.pyrcnt[l] = h->pyrcnt[l];
       ip.lv[l] = h->lv[l];
     }
@@ -434,8 +430,7 @@ static int enqueue_group(youth_cuda_handle* h, const uint16_t* const* raw_dev, i
     memset(&np, 0, sizeof(np));
     int total = 0;
     for (int l = 0; l < c.levels; ++l) {
-      np.vmap[l] = h->vmap[l];
-      np.nmap[l] = h->nmap[l];
+      np.maps[l] = h->maps[l];
       np.lv[l] = h->lv[l];
       total += h->npix[l];
     }
@@ -646,29 +641,40 @@ extern "C" int youth_cuda_debug_read(youth_cuda_handle* h, int what, int stream,
       return 1;
     case YOUTH_DBG_VERTEX:
     case YOUTH_DBG_NORMAL:
-      if (dst_bytes < np * 16) return fail("dst too small");
-      CU(cudaMemcpy(dst, (what == YOUTH_DBG_VERTEX ? h->vmap[level] : h->nmap[level]) + off, np * 16,
-                    cudaMemcpyDeviceToHost));
+    case YOUTH_DBG_MASK: {
+      /* the device keeps six float planes per slot; the read-back presents them as the
+       * float4 (x, y, z, valid) maps / validity mask of the specification */
+      if (dst_bytes < (what == YOUTH_DBG_MASK ? np : np * 16)) return fail("dst too small");
+      float* tmp = (float*)malloc(np * 6 * sizeof(float));
+      if (!tmp) return fail("host allocation failed");
+      cudaError_t e = cudaMemcpy(tmp, h->maps[level] + ((size_t)stream * h->R + slot) * 6 * np, np * 6 * sizeof(float),
+                                 cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) {
+        free(tmp);
+        return fail("map read-back failed: %s", cudaGetErrorString(e));
+      }
+      for (size_t i = 0; i < np; ++i) {
+        const float vx = tmp[i], vy = tmp[np + i], vz = tmp[2 * np + i];
+        const float nx = tmp[3 * np + i], ny = tmp[4 * np + i], nz = tmp[5 * np + i];
+        const int vok = vz > 0.0f, nok = (nx != 0.0f || ny != 0.0f || nz != 0.0f);
+        if (what == YOUTH_DBG_MASK) {
+          ((uint8_t*)dst)[i] = (uint8_t)(vok | (nok << 1));
+        } else {
+          float* o = (float*)dst + 4 * i;
+          if (what == YOUTH_DBG_VERTEX) {
+            o[0] = vx; o[1] = vy; o[2] = vz; o[3] = vok ? 1.0f : 0.0f;
+          } else {
+            o[0] = nx; o[1] = ny; o[2] = nz; o[3] = nok ? 1.0f : 0.0f;
+          }
+        }
+      }
+      free(tmp);
       return 1;
+    }
     case YOUTH_DBG_PYRCNT:
       if (dst_bytes < np) return fail("dst too small");
       CU(cudaMemcpy(dst, h->pyrcnt[level] + off, np, cudaMemcpyDeviceToHost));
       return 1;
-    case YOUTH_DBG_MASK: {
-      if (dst_bytes < np) return fail("dst too small");
-      float4* tmp = (float4*)malloc(np * 16 * 2);
-      if (!tmp) return fail("host allocation failed");
-      cudaError_t e = cudaMemcpy(tmp, h->vmap[level] + off, np * 16, cudaMemcpyDeviceToHost);
-      if (e == cudaSuccess) e = cudaMemcpy(tmp + np, h->nmap[level] + off, np * 16, cudaMemcpyDeviceToHost);
-      if (e != cudaSuccess) {
-        free(tmp);
-        return fail("mask read-back failed: %s", cudaGetErrorString(e));
-      }
-      uint8_t* m = (uint8_t*)dst;
-      for (size_t i = 0; i < np; ++i) m[i] = (uint8_t)((tmp[i].w != 0.f ? 1 : 0) | (tmp[np + i].w != 0.f ? 2 : 0));
-      free(tmp);
-      return 1;
-    }
     default:
       return fail("unknown debug selector %d", what);
   }
