@@ -5,7 +5,7 @@
  *
  * Device-resident state per handle (all in HBM, sized at init, nothing allocated per frame):
  *   ring      per stream R = batch+1 slots; per slot and pyramid level: float depth,
- *             six float planes vx vy vz nx ny nz (24 B/pixel), uint8 pyramid count
+ *             three float2 planes (vx,vy) (vz,nx) (ny,nz) (24 B/pixel), uint8 pyramid count
  *   raw       2 x [S][batch] uint16 frames (double-buffered H2D landing zone)
  *   pairs     per (stream, frame-in-group): double+float relative pose, per-run partial
  *             sums [max_runs][32] float, reduced sums [32] double, status
@@ -57,7 +57,7 @@ struct youth_cuda_handle {
   bool own_stream;
   /* ring */
   float* depth[YOUTH_MAX_LEVELS];
-  float* maps[YOUTH_MAX_LEVELS]; /* [S][R][6][npix]: vx vy vz nx ny nz planes */
+  float2* maps[YOUTH_MAX_LEVELS]; /* [S][R][3][npix]: (vx,vy) (vz,nx) (ny,nz) planes */
   uint8_t* pyrcnt[YOUTH_MAX_LEVELS];
   /* raw landing zone */
   uint16_t* raw[2];
@@ -278,7 +278,7 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
   const size_t slots = (size_t)h->S * h->R;
   for (int l = 0; l < cfg->levels; ++l) {
     CU(dalloc(&h->depth[l], slots * h->npix[l]));
-    CU(dalloc(&h->maps[l], slots * 6 * h->npix[l]));
+    CU(dalloc(&h->maps[l], slots * 3 * h->npix[l]));
     CU(dalloc(&h->pyrcnt[l], slots * h->npix[l]));
   }
   const size_t frame_px = (size_t)cfg->width * cfg->height;
@@ -642,20 +642,20 @@ extern "C" int youth_cuda_debug_read(youth_cuda_handle* h, int what, int stream,
     case YOUTH_DBG_VERTEX:
     case YOUTH_DBG_NORMAL:
     case YOUTH_DBG_MASK: {
-      /* the device keeps six float planes per slot; the read-back presents them as the
+      /* the device keeps three float2 planes per slot; the read-back presents them as the
        * float4 (x, y, z, valid) maps / validity mask of the specification */
       if (dst_bytes < (what == YOUTH_DBG_MASK ? np : np * 16)) return fail("dst too small");
       float* tmp = (float*)malloc(np * 6 * sizeof(float));
       if (!tmp) return fail("host allocation failed");
-      cudaError_t e = cudaMemcpy(tmp, h->maps[level] + ((size_t)stream * h->R + slot) * 6 * np, np * 6 * sizeof(float),
+      cudaError_t e = cudaMemcpy(tmp, h->maps[level] + ((size_t)stream * h->R + slot) * 3 * np, np * 6 * sizeof(float),
                                  cudaMemcpyDeviceToHost);
       if (e != cudaSuccess) {
         free(tmp);
         return fail("map read-back failed: %s", cudaGetErrorString(e));
       }
       for (size_t i = 0; i < np; ++i) {
-        const float vx = tmp[i], vy = tmp[np + i], vz = tmp[2 * np + i];
-        const float nx = tmp[3 * np + i], ny = tmp[4 * np + i], nz = tmp[5 * np + i];
+        const float vx = tmp[2 * i], vy = tmp[2 * i + 1], vz = tmp[2 * np + 2 * i];
+        const float nx = tmp[2 * np + 2 * i + 1], ny = tmp[4 * np + 2 * i], nz = tmp[4 * np + 2 * i + 1];
         const int vok = vz > 0.0f, nok = (nx != 0.0f || ny != 0.0f || nz != 0.0f);
         if (what == YOUTH_DBG_MASK) {
           ((uint8_t*)dst)[i] = (uint8_t)(vok | (nok << 1));
