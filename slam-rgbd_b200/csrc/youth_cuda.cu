@@ -22,6 +22,9 @@
 #include "youth_cuda.h"
 #include "youth_kernels.cuh"
 
+#define YK_CHUNK_FRAMES 16 /* host-fed groups are copied + preprocessed in chunks of at least this many frames */
+#define YK_MAX_CHUNKS 64
+
 /* ------------------------------------------------------------------ errors */
 
 static thread_local char g_err[512] = "";
@@ -62,7 +65,7 @@ struct youth_cuda_handle {
   /* raw landing zone */
   uint16_t* raw[2];
   uint16_t* pinned[2];
-  cudaEvent_t raw_free[2], raw_ready[2];
+  cudaEvent_t raw_free[2], chunk_ready[2][YK_MAX_CHUNKS];
   bool raw_used[2];
   int raw_turn;
   /* bilateral tables */
@@ -198,7 +201,8 @@ extern "C" void youth_cuda_destroy(youth_cuda_handle* h) {
     cudaFree(h->raw[k]);
     if (h->pinned[k]) cudaFreeHost(h->pinned[k]);
     if (h->raw_free[k]) cudaEventDestroy(h->raw_free[k]);
-    if (h->raw_ready[k]) cudaEventDestroy(h->raw_ready[k]);
+    for (int c2 = 0; c2 < YK_MAX_CHUNKS; ++c2)
+      if (h->chunk_ready[k][c2]) cudaEventDestroy(h->chunk_ready[k][c2]);
   }
   cudaFree(h->wr);
   cudaFree(h->pose_d);
@@ -286,7 +290,7 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
     CU(dalloc(&h->raw[k], (size_t)h->P * frame_px));
     CU(cudaHostAlloc((void**)&h->pinned[k], (size_t)h->P * frame_px * sizeof(uint16_t), cudaHostAllocDefault));
     CU(cudaEventCreateWithFlags(&h->raw_free[k], cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&h->raw_ready[k], cudaEventDisableTiming));
+    for (int c2 = 0; c2 < YK_MAX_CHUNKS; ++c2) CU(cudaEventCreateWithFlags(&h->chunk_ready[k][c2], cudaEventDisableTiming));
   }
   /* bilateral tables (the only libm use; depends on the config alone) */
   {
@@ -389,11 +393,12 @@ static IcpParams icp_params(const youth_cuda_handle* h, int level, const RingGeo
   return ip;
 }
 
-/* enqueue the whole schedule for n frames of every stream; raw_dev[s] = device pointers */
-static int enqueue_group(youth_cuda_handle* h, const uint16_t* const* raw_dev, int n) {
+/* stages 1 + 2 for frames [frame0, frame0 + cn) of every stream's group of n frames; raw_dev[s] points at
+ * the first frame of the GROUP.  Chunks let host-fed groups overlap their H2D copies with ingest. */
+static int enqueue_preprocess(youth_cuda_handle* h, const uint16_t* const* raw_dev, int n, int frame0, int cn) {
   const youth_cuda_config& c = h->cfg;
   const RingGeom ring = ring_of(h, n);
-  const int frames = h->S * n;
+  const int frames = h->S * cn;
   /* stage 1 + 2a */
   {
     IngestParams ip;
@@ -409,6 +414,8 @@ static int enqueue_group(youth_cuda_handle* h, const uint16_t* const* raw_dev, i
     ip.pose_f = h->pose_f;
     ip.pair_status = h->pair_status;
     ip.ring = ring;
+    ip.frame0 = frame0;
+    ip.chunk_n = cn;
     ip.levels = c.levels;
     ip.dmin = c.depth_min_mm;
     ip.dmax = c.depth_max_mm;
@@ -435,11 +442,22 @@ static int enqueue_group(youth_cuda_handle* h, const uint16_t* const* raw_dev, i
       total += h->npix[l];
     }
     np.ring = ring;
+    np.frame0 = frame0;
+    np.chunk_n = cn;
     np.levels = c.levels;
     dim3 grid((total + 255) / 256, frames);
     ProfScope ps(h, YOUTH_PROF_NORMALS);
     k_normals<<<grid, 256, 0, h->stream>>>(np);
   }
+  CU(cudaGetLastError());
+  return 1;
+}
+
+/* stages 3-5 + pose chain for a whole group of n frames per stream */
+static int enqueue_icp(youth_cuda_handle* h, int n) {
+  const youth_cuda_config& c = h->cfg;
+  const RingGeom ring = ring_of(h, n);
+  const int frames = h->S * n;
   /* stages 3-5: coarse to fine, fixed iteration schedule, one launch per iteration, no host sync */
   for (int level = c.levels - 1; level >= 0; --level) {
     const IcpParams ip = icp_params(h, level, ring);
@@ -481,7 +499,8 @@ extern "C" int youth_cuda_track_batch(youth_cuda_handle* h, const uint16_t* cons
   const uint16_t* dev_ptrs[YK_MAX_STREAMS];
   if (mem_kind == YOUTH_MEM_DEVICE) {
     for (int s = 0; s < h->S; ++s) dev_ptrs[s] = depth[s];
-    if (!enqueue_group(h, dev_ptrs, n_frames)) return 0;
+    if (!enqueue_preprocess(h, dev_ptrs, n_frames, 0, n_frames)) return 0;
+    if (!enqueue_icp(h, n_frames)) return 0;
   } else if (mem_kind == YOUTH_MEM_HOST || mem_kind == YOUTH_MEM_HOST_PINNED) {
     const int k = h->raw_turn;
     h->raw_turn ^= 1;
@@ -491,20 +510,29 @@ extern "C" int youth_cuda_track_batch(youth_cuda_handle* h, const uint16_t* cons
         CU(cudaEventSynchronize(h->raw_free[k])); /* the pinned staging copy is about to be overwritten */
       CU(cudaStreamWaitEvent(h->copy_stream, h->raw_free[k], 0));
     }
-    for (int s = 0; s < h->S; ++s) {
-      uint16_t* dst = h->raw[k] + (size_t)s * n_frames * frame_px;
-      const uint16_t* src = depth[s];
-      if (mem_kind == YOUTH_MEM_HOST) {
-        uint16_t* stage = h->pinned[k] + (size_t)s * n_frames * frame_px;
-        memcpy(stage, src, seq_bytes); /* synchronous copy: the caller may reuse its buffer (SLAM.cpp:133-134) */
-        src = stage;
+    /* copy and preprocess in chunks: the H2D of chunk c+1 overlaps ingest of chunk c */
+    int ch = (n_frames + YK_MAX_CHUNKS - 1) / YK_MAX_CHUNKS;
+    if (ch < YK_CHUNK_FRAMES) ch = YK_CHUNK_FRAMES;
+    for (int s = 0; s < h->S; ++s) dev_ptrs[s] = h->raw[k] + (size_t)s * n_frames * frame_px;
+    int ci = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += ch, ++ci) {
+      const int cn = n_frames - f0 < ch ? n_frames - f0 : ch;
+      const size_t off = (size_t)f0 * frame_px, bytes = (size_t)cn * frame_px * sizeof(uint16_t);
+      for (int s = 0; s < h->S; ++s) {
+        uint16_t* dst = h->raw[k] + (size_t)s * n_frames * frame_px + off;
+        const uint16_t* src = depth[s] + off;
+        if (mem_kind == YOUTH_MEM_HOST) {
+          uint16_t* stage = h->pinned[k] + (size_t)s * n_frames * frame_px + off;
+          memcpy(stage, src, bytes); /* synchronous copy: the caller may reuse its buffer (SLAM.cpp:133-134) */
+          src = stage;
+        }
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
       }
-      CU(cudaMemcpyAsync(dst, src, seq_bytes, cudaMemcpyHostToDevice, h->copy_stream));
-      dev_ptrs[s] = dst;
+      CU(cudaEventRecord(h->chunk_ready[k][ci], h->copy_stream));
+      CU(cudaStreamWaitEvent(h->stream, h->chunk_ready[k][ci], 0));
+      if (!enqueue_preprocess(h, dev_ptrs, n_frames, f0, cn)) return 0;
     }
-    CU(cudaEventRecord(h->raw_ready[k], h->copy_stream));
-    CU(cudaStreamWaitEvent(h->stream, h->raw_ready[k], 0));
-    if (!enqueue_group(h, dev_ptrs, n_frames)) return 0;
+    if (!enqueue_icp(h, n_frames)) return 0;
     CU(cudaEventRecord(h->raw_free[k], h->stream));
     h->raw_used[k] = true;
   } else {
