@@ -145,7 +145,7 @@ void yo_bilateral(const yo_config* c, const uint16_t* raw, float* out) {
           if (diff > cut) continue;
           const float w = ws[dy + 3][dx + 3] * wr[diff];
           sw = sw + w;
-          swd = swd + w * (float)dk;
+          swd = fmaf(w, (float)dk, swd); /* specified fused multiply-add */
         }
       }
       out[y * W + x] = swd / sw; /* centre tap has weight ws[3][3]*wr[0] = 1, so sw >= 1 */

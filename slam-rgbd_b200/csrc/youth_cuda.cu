@@ -439,15 +439,18 @@ static int enqueue_preprocess(youth_cuda_handle* h, const uint16_t* const* raw_d
     for (int l = 0; l < c.levels; ++l) {
       np.maps[l] = h->maps[l];
       np.lv[l] = h->lv[l];
-      total += h->npix[l];
+      if (l >= 1) total += h->npix[l];
     }
+    np.first_level = 1;
     np.ring = ring;
     np.frame0 = frame0;
     np.chunk_n = cn;
     np.levels = c.levels;
-    dim3 grid((total + 255) / 256, frames);
-    ProfScope ps(h, YOUTH_PROF_NORMALS);
-    k_normals<<<grid, 256, 0, h->stream>>>(np);
+    if (total > 0) {
+      dim3 grid((total + 255) / 256, frames);
+      ProfScope ps(h, YOUTH_PROF_NORMALS);
+      k_normals<<<grid, 256, 0, h->stream>>>(np);
+    }
   }
   CU(cudaGetLastError());
   return 1;
