@@ -410,7 +410,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="frames per launch group")
+    ap.add_argument("--batch", type=int, default=300, help="frames per launch group (300 = the whole sequence)")
     ap.add_argument("--ppt", type=int, default=0, help="override icp_ppt (reduction geometry; 0 = library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -481,7 +481,7 @@ static int enqueue_icp(youth_cuda_handle* h, int n) {
     cp.last_inliers = h->last_inliers;
     cp.cap = c.traj_capacity;
     ProfScope ps(h, YOUTH_PROF_MISC);
-    k_compose<<<(h->S + 63) / 64, 64, 0, h->stream>>>(cp);
+    k_compose<<<h->S, 128, 0, h->stream>>>(cp);
   }
   CU(cudaGetLastError());
   if (h->prof_on && h->prof_n > h->prof_cap - 256) return prof_flush(h);
