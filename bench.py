@@ -386,8 +386,10 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "k_icp (level 0)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
                      "avg_launch_ms": icp0_ms, "algorithmic_bytes_per_launch": bytes_per_launch,
-                     "note": "algorithmic 48 B/px/iter; maps are float4-padded and L2-resident across "
-                             "iterations, see DESIGN.md section 5"},
+                     "note": "algorithmic 48 B/px/iter = the bytes k_icp requests (three float2 planes per frame, "
+                             "24 B/px); each frame's second use in a launch hits L2, so DRAM traffic is about half "
+                             "(traffic = ncu dram bytes per launch, profiles/traffic.json); a fraction above 1 is L2 reuse, "
+                             "see DESIGN.md section 5"},
         "per_kernel_ms_per_step": step_prof,
         "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": threads, "kind": "port",
                          "sample": f"{threads} threads x {fpt} consecutive frames ({cpu_kind}), {cpu_wall:.1f}s wall"},
