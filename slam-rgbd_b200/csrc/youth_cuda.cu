@@ -687,7 +687,7 @@ extern "C" int youth_cuda_debug_read(youth_cuda_handle* h, int what, int stream,
       for (size_t i = 0; i < np; ++i) {
         const float vx = tmp[2 * i], vy = tmp[2 * i + 1], vz = tmp[2 * np + 2 * i];
         const float nx = tmp[2 * np + 2 * i + 1], ny = tmp[4 * np + 2 * i], nz = tmp[4 * np + 2 * i + 1];
-        const int vok = vz > 0.0f, nok = (nx != 0.0f || ny != 0.0f || nz != 0.0f);
+        const int vok = vz > 0.0f, nok = YK_N_VALID(nx);
         if (what == YOUTH_DBG_MASK) {
           ((uint8_t*)dst)[i] = (uint8_t)(vok | (nok << 1));
         } else {
@@ -695,7 +695,7 @@ extern "C" int youth_cuda_debug_read(youth_cuda_handle* h, int what, int stream,
           if (what == YOUTH_DBG_VERTEX) {
             o[0] = vx; o[1] = vy; o[2] = vz; o[3] = vok ? 1.0f : 0.0f;
           } else {
-            o[0] = nx; o[1] = ny; o[2] = nz; o[3] = nok ? 1.0f : 0.0f;
+            o[0] = nok ? nx : 0.0f; o[1] = ny; o[2] = nz; o[3] = nok ? 1.0f : 0.0f;
           }
         }
       }

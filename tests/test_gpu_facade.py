@@ -99,6 +99,55 @@ def test_algorithm_module_replays_bin(pkg, small_seq, tmp_path):
     assert np.abs(rows[:, 1:4] - gt_rows[:, 1:4]).max() < 2e-3
 
 
+def test_live_path_reference_chunks_to_tracker(pkg, small_seq):
+    """(f)1 live path: frames leave through the REFERENCE's own sendMetadata/sendDataInChunks
+    (oracle/_ref, compiled from loggingModule.c) over a real POSIX mq, are reassembled by
+    youth_reasm_feed (the hook INTEGRATION.md section 3 describes) and pushed into
+    processSlamFrame at the reference's frame-complete point; the trajectory must equal
+    tracking the same frames directly."""
+    ref_so = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libref_logging.so")
+    if not os.path.exists(ref_so):
+        pytest.skip("oracle/_ref/libref_logging.so not built")
+    ref = C.CDLL(ref_so)
+    ref.ref_chunk_stream.argtypes = [C.c_char_p, C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int]
+    frames, _ = small_seq
+    host = pkg.host_lib()
+    host.youthSlamSetOptions(1, 2)
+    host.initSlamModule(None, None)
+    assert host.isSlamModuleRunning() == 1
+    reasm = host.youth_reasm_create()
+    color = np.full((480, 640, 3), 128, dtype=np.uint8)
+    msgs = np.zeros((200, 8192), dtype=np.uint8)
+    lens = np.zeros(200, dtype=np.int32)
+    for i in range(4):
+        n = ref.ref_chunk_stream(b"/youth_live_mq_%d" % os.getpid(), i, 33 * i, 640, 480, frames[i].ctypes.data,
+                                 color.ctypes.data, msgs.ctypes.data, lens.ctypes.data, 200)
+        if n < 0:
+            host.stopSlamModule()
+            pytest.skip("POSIX message queues unavailable")
+        assert n == 196
+        completed = 0
+        for k in range(n):
+            if host.youth_reasm_feed(reasm, msgs[k].ctypes.data, int(lens[k])) == 1:  # loggingModule.c:354
+                completed += 1
+                w, h, fid, ts = C.c_int(), C.c_int(), C.c_int(), C.c_uint32()
+                host.youth_reasm_info(reasm, C.byref(w), C.byref(h), C.byref(fid), C.byref(ts))
+                assert (w.value, h.value, fid.value, ts.value) == (640, 480, i, 33 * i)
+                assert host.processSlamFrame(host.youth_reasm_depth(reasm), host.youth_reasm_color(reasm), w.value,
+                                             h.value, ts.value) == 1
+        assert completed == 1
+    host.youthSlamDrain()
+    poses = np.empty((4, 12), dtype=np.float32)
+    assert host.youthSlamGetTrajectory(poses.ctypes.data, None, None, 4) == 4
+    host.youth_reasm_destroy(reasm)
+    host.stopSlamModule()
+    direct = make_tracker(pkg, batch=4)
+    want = direct.track_batch([frames[:4]])[0]
+    direct.close()
+    assert np.array_equal(poses.view(np.uint32), want.view(np.uint32))
+
+
 def test_golden_fixture_through_cabi(pkg):
     from slam_rgbd_b200 import binding as B
 
