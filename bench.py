@@ -164,14 +164,24 @@ def host_threads():
 
 
 def base_config_dict(args, n_gpus):
+    spg = getattr(args, "sequences_per_gpu", 1)
+    w, h, lv = getattr(args, "width", W), getattr(args, "height", H), getattr(args, "levels", 3)
+    if (w, h, lv, spg) == (W, H, 3, 1):
+        name = "configs[1]"
+    elif (w, h, lv) == (W, H, 3):
+        name = "configs[3]-style (several sequences per GPU)"
+    else:
+        name = "configs[4]-style (high resolution)"
+    iters = "/".join(str(x) for x in [10, 5, 4, 4][:lv])
+    raw_mb = spg * FRAMES * w * h * 2 / 1e6
     return {
-        "workload": "configs[1]: synthetic 640x480 uint16 depth sequence, 300 frames, 3-level pyramid, "
-                    "ICP iterations L0/L1/L2 = 10/5/4, 7x7 bilateral on, one sequence per GPU",
-        "frames_per_step_per_gpu": FRAMES,
+        "workload": f"{name}: synthetic {w}x{h} uint16 depth sequence, 300 frames, {lv}-level pyramid, "
+                    f"ICP iterations fine->coarse = {iters}, 7x7 bilateral on, {spg} sequence(s) per GPU",
+        "frames_per_step_per_gpu": FRAMES * spg,
         "batch_frames_per_launch_group": args.batch,
-        "sequences_per_gpu": 1,
-        "partition": f"{n_gpus} independent sequence(s), one per GPU, no data-path collective",
-        "l2": "inputs (184 MB raw depth per step) exceed the 126 MB L2 and are streamed once per step; "
+        "sequences_per_gpu": spg,
+        "partition": f"{n_gpus * spg} independent sequence(s), {spg} per GPU, no data-path collective",
+        "l2": f"inputs ({raw_mb:.0f} MB raw depth per step) exceed the 126 MB L2 and are streamed once per step; "
               "no explicit flush",
     }
 
@@ -238,15 +248,19 @@ def run_ours(args):
 
     stream = torch.cuda.Stream()
     extra = {"icp_ppt": args.ppt} if args.ppt else {}
-    cfg = pkg.default_config(batch=args.batch, n_streams=1, device=local, traj_capacity=FRAMES,
+    Wd, Hd, S = args.width, args.height, args.sequences_per_gpu
+    if (Wd, Hd) != (W, H):
+        extra.update(width=Wd, height=Hd, fx=570.3 * Wd / 640, fy=570.3 * Wd / 640, cx=Wd / 2.0, cy=Hd / 2.0)
+    cfg = pkg.default_config(batch=args.batch, n_streams=S, device=local, traj_capacity=FRAMES, levels=args.levels,
                              stream=stream.cuda_stream, **extra)
     trk = B.Tracker(cfg)
 
-    # one independent sequence per rank (seed 20261018 + rank)
+    # independent sequences: rank r tracks sequences r*S .. r*S+S-1 (seed 20261018 + sequence)
     t0 = time.perf_counter()
-    frames = pkg.synth_sequence(FRAMES, W, H, sequence=rank)
-    log(f"[rank {rank}] generated {FRAMES} frames in {time.perf_counter() - t0:.1f}s")
-    frame_bytes = W * H * 2
+    frames = np.stack([pkg.synth_sequence(FRAMES, Wd, Hd, sequence=rank * S + k) for k in range(S)])
+    log(f"[rank {rank}] generated {S} x {FRAMES} frames in {time.perf_counter() - t0:.1f}s")
+    frame_bytes = Wd * Hd * 2
+    seq_bytes = FRAMES * frame_bytes
     d_frames = torch.from_numpy(frames.view(np.int16)).to(f"cuda:{local}")
     d_base = d_frames.data_ptr()
     # pinned host copy for the e2e arm
@@ -262,27 +276,28 @@ def run_ours(args):
             pass
         holder = _Ptr()
         holder.__cuda_array_interface__ = {
-            "shape": (FRAMES, 12), "typestr": "<f4", "version": 3,
+            "shape": (S, FRAMES, 12), "typestr": "<f4", "version": 3,  # traj_capacity == FRAMES: streams are contiguous
             "data": (trk.lib.youth_cuda_trajectory_device_ptr(trk.h, 0), False)}
         traj_view = torch.as_tensor(holder, device=f"cuda:{local}")
-        gathered = torch.empty((world, FRAMES, 12), dtype=torch.float32, device=f"cuda:{local}")
+        gathered = torch.empty((world, S, FRAMES, 12), dtype=torch.float32, device=f"cuda:{local}")
 
     def step_device():
         trk.reset()
         for a, n in groups:
-            trk.track_batch_ptrs([d_base + a * frame_bytes], n, B.MEM_DEVICE)
+            trk.track_batch_ptrs([d_base + k * seq_bytes + a * frame_bytes for k in range(S)], n, B.MEM_DEVICE)
         if dist is not None:
             with torch.cuda.stream(stream):
                 dist.all_gather_into_tensor(gathered, traj_view)
 
-    host_traj = np.empty((FRAMES, 12), dtype=np.float32)
+    host_traj = np.empty((S, FRAMES, 12), dtype=np.float32)
 
     def step_e2e():
         trk.reset()
         for a, n in groups:
-            trk.track_batch_ptrs([pin_ptr + a * frame_bytes], n, B.MEM_HOST_PINNED)
-        got = trk.lib.youth_cuda_get_trajectory(trk.h, 0, 0, FRAMES, host_traj.ctypes.data, None, None)
-        assert got == FRAMES
+            trk.track_batch_ptrs([pin_ptr + k * seq_bytes + a * frame_bytes for k in range(S)], n, B.MEM_HOST_PINNED)
+        for k in range(S):
+            got = trk.lib.youth_cuda_get_trajectory(trk.h, k, 0, FRAMES, host_traj[k].ctypes.data, None, None)
+            assert got == FRAMES
 
     def barrier():
         trk.sync()
@@ -313,11 +328,11 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
-    value = world * FRAMES / (ms_per_step * 1e-3)
+    value = world * S * FRAMES / (ms_per_step * 1e-3)
 
     # pose error vs synthetic ground truth (reported, not part of the timed region)
     poses, _, status = trk.trajectory()
-    gt = pkg.synth_gt(FRAMES, W, H, sequence=rank)
+    gt = pkg.synth_gt(FRAMES, Wd, Hd, sequence=rank * S)
     terr = np.linalg.norm(poses.reshape(-1, 3, 4)[:, :, 3] - gt.reshape(-1, 3, 4)[:, :, 3], axis=1)
     lost = int((status & B.STATUS_LOST != 0).sum())
 
@@ -331,11 +346,12 @@ def run_ours(args):
     trk.sync()
     e2e_s = time.perf_counter() - t0
     if dist is not None:
+        torch.cuda.synchronize()
         t = torch.tensor([e2e_s], device=f"cuda:{local}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = world * FRAMES * args.steps / e2e_s
-    poses_e2e = host_traj.copy()
+    e2e_value = world * S * FRAMES * args.steps / e2e_s
+    poses_e2e = host_traj[0].copy()
     e2e_matches = bool(np.array_equal(poses_e2e.view(np.uint32), poses.view(np.uint32)))
 
     # ---- per-kernel timing (separate profiled step: events around every launch)
@@ -354,8 +370,8 @@ def run_ours(args):
     icp0_ms = prof_ms[B.PROF_ICP0] / max(1, int(prof_n[B.PROF_ICP0]))
     # launches differ in pairs per launch (last group is shorter): use the average pairs per launch
     icp0_launches = int(prof_n[B.PROF_ICP0])
-    pairs_total = FRAMES * cfg.iters[0]
-    bytes_per_launch = ALG_BYTES_PER_PX_ITER * W * H * pairs_total / max(1, icp0_launches)
+    pairs_total = S * FRAMES * cfg.iters[0]
+    bytes_per_launch = ALG_BYTES_PER_PX_ITER * Wd * Hd * pairs_total / max(1, icp0_launches)
     achieved = bytes_per_launch / (icp0_ms * 1e-3) / 1e9 if icp0_ms > 0 else 0.0
     names = {B.PROF_INGEST: "k_ingest", B.PROF_NORMALS: "k_normals", B.PROF_ICP0: "k_icp_L0",
              B.PROF_ICP0 + 1: "k_icp_L1", B.PROF_ICP0 + 2: "k_icp_L2", B.PROF_ICP0 + 3: "k_icp_L3",
@@ -363,16 +379,33 @@ def run_ours(args):
     step_prof = {names[i]: {"ms": round(float(prof_ms[i]), 4), "launches": int(prof_n[i])}
                  for i in range(B.PROF_CLASSES) if prof_n[i]}
 
-    traffic = None
+    traffic = None  # ncu DRAM bytes per launch: only valid for the configuration it was captured on
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("k_icp_L0_dram_bytes_per_launch")
+            tj = json.load(f)
+        if (Wd, Hd, S, args.levels) == (W, H, 1, 3) and tj.get("pairs_per_launch") == args.batch:
+            traffic = tj.get("k_icp_L0_dram_bytes_per_launch")
     except Exception:
         pass
 
+    # ---- live mode: one frame per call (youth_cuda_track), pose read back every frame
+    streaming = None
+    if (Wd, Hd, S) == (W, H, 1):
+        live = B.Tracker(pkg.default_config(batch=1, device=local, traj_capacity=128, levels=args.levels))
+        for i in range(8):
+            live.track(frames[0][i], ts=33 * i)
+        t0 = time.perf_counter()
+        nlive = 100
+        for i in range(nlive):
+            live.track(frames[0][8 + i], ts=33 * (8 + i))
+        dt = time.perf_counter() - t0
+        live.close()
+        streaming = {"frames_per_sec": nlive / dt, "us_per_frame": dt / nlive * 1e6,
+                     "what": "youth_cuda_track: one pageable host frame in, blocking pose out, batch 1"}
+
     threads = max(1, min(host_threads(), 32))
-    fpt = 61  # 60 frame pairs per thread: about 10-15 s of CPU work per thread
-    cpu_fps, cpu_wall, cpu_kind = cpu_oracle_fps(frames, cfg, threads, fpt)
+    fpt = max(3, int(61 * (W * H) / (Wd * Hd)))  # 60 frame pairs per thread at 640x480: about 10-15 s of CPU work
+    cpu_fps, cpu_wall, cpu_kind = cpu_oracle_fps(frames[0], cfg, threads, fpt)
 
     line = {
         "metric": "icp_tracked_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
@@ -380,8 +413,8 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": base_config_dict(args, world),
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": FRAMES * frame_bytes,
-                "d2h_bytes_per_step": FRAMES * 48, "bit_identical_to_device_arm": e2e_matches},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": S * FRAMES * frame_bytes,
+                "d2h_bytes_per_step": S * FRAMES * 48, "bit_identical_to_device_arm": e2e_matches},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_icp (level 0)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
@@ -396,6 +429,7 @@ def run_ours(args):
         "pose_error_vs_ground_truth": {"max_translation_m": float(terr.max()), "final_translation_m": float(terr[-1]),
                                        "frames_flagged_lost": lost},
         "frames_per_sec_per_gpu": value / world,
+        "streaming_single_frame": streaming,
     }
     print(json.dumps(line), flush=True)
     C.cast(pin_ptr, C.c_void_p)
@@ -414,6 +448,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=300, help="frames per launch group (300 = the whole sequence)")
     ap.add_argument("--ppt", type=int, default=0, help="override icp_ppt (reduction geometry; 0 = library default)")
+    ap.add_argument("--sequences-per-gpu", type=int, default=1, help="independent sequences tracked per GPU (configs[3] uses 8)")
+    ap.add_argument("--width", type=int, default=W)
+    ap.add_argument("--height", type=int, default=H)
+    ap.add_argument("--levels", type=int, default=3)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -420,7 +420,9 @@ static int enqueue_preprocess(youth_cuda_handle* h, const uint16_t* const* raw_d
     ip.dmin = c.depth_min_mm;
     ip.dmax = c.depth_max_mm;
     ip.range_cut = h->range_cut;
-    memcpy(ip.ws, h->ws, sizeof(ip.ws));
+    for (int dy = 0; dy < 7; ++dy)
+      for (int k = 0; k < 8; ++k)
+        ip.wsp[dy * 8 + k] = make_float2(k <= 6 ? h->ws[dy * 7 + k] : 0.0f, k >= 1 ? h->ws[dy * 7 + k - 1] : 0.0f);
     ip.wr = h->wr;
     ip.depth_factor = c.depth_factor;
     ip.pyr_thr = 3.0f * c.sigma_range_mm;
