@@ -391,7 +391,8 @@ def run_ours(args):
     # ---- live mode: one frame per call (youth_cuda_track), pose read back every frame
     streaming = None
     if (Wd, Hd, S) == (W, H, 1):
-        live = B.Tracker(pkg.default_config(batch=1, device=local, traj_capacity=128, levels=args.levels))
+        live = B.Tracker(pkg.default_config(batch=1, device=local, traj_capacity=128, levels=args.levels,
+                                            **({"icp_ppt": args.ppt} if args.ppt else {})))
         for i in range(8):
             live.track(frames[0][i], ts=33 * i)
         t0 = time.perf_counter()
@@ -406,6 +407,8 @@ def run_ours(args):
     threads = max(1, min(host_threads(), 32))
     fpt = max(3, int(61 * (W * H) / (Wd * Hd)))  # 60 frame pairs per thread at 640x480: about 10-15 s of CPU work
     cpu_fps, cpu_wall, cpu_kind = cpu_oracle_fps(frames[0], cfg, threads, fpt)
+    cpu1_fps, _, _ = cpu_oracle_fps(frames[0], cfg, 1, max(3, fpt // 6))               # one thread, speed build
+    cpu1p_fps, _, _ = cpu_oracle_fps(frames[0], cfg, 1, max(3, fpt // 6), fast=False)  # one thread, parity build
 
     line = {
         "metric": "icp_tracked_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
@@ -425,7 +428,8 @@ def run_ours(args):
                              "see DESIGN.md section 5"},
         "per_kernel_ms_per_step": step_prof,
         "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": f"{threads} threads x {fpt} consecutive frames ({cpu_kind}), {cpu_wall:.1f}s wall"},
+                         "sample": f"{threads} threads x {fpt} consecutive frames ({cpu_kind}), {cpu_wall:.1f}s wall",
+                         "single_thread_value": cpu1_fps, "single_thread_parity_build_value": cpu1p_fps},
         "pose_error_vs_ground_truth": {"max_translation_m": float(terr.max()), "final_translation_m": float(terr[-1]),
                                        "frames_flagged_lost": lost},
         "frames_per_sec_per_gpu": value / world,

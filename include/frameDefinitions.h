@@ -76,7 +76,17 @@ typedef struct {
 
 #define MAX_MSG_SIZE 8192
 
-/* ---- additions (not in the reference): derived constants + layout pins ---- */
+/* ---- additions (not in the reference): pose egress message, derived constants, layout pins ---- */
+/* Next free message type after MSG_TYPE_CONTROL: one message =
+ * MessageHeader (frameId / timestamp of the tracked frame, dataSize = sizeof(YouthPoseMsg)) +
+ * YouthPoseMsg.  Old viewers ignore unknown types (viewerModule.c:197-248 switches on 1..3). */
+#define MSG_TYPE_POSE 5
+typedef struct {
+  float pose[12];   /* camera-to-world, row-major 3x4 [R|t], world = first camera frame */
+  uint32_t status;  /* YOUTH_STATUS_* bits */
+  uint32_t inliers; /* correspondences of the last ICP iteration at the finest level */
+} YouthPoseMsg;
+
 #define YOUTH_CHUNK_PAYLOAD ((int)(MAX_MSG_SIZE - sizeof(MessageHeader))) /* 7900 */
 #define YOUTH_CHUNKS_FOR(bytes) (((bytes) + YOUTH_CHUNK_PAYLOAD - 1) / YOUTH_CHUNK_PAYLOAD)
 
@@ -94,5 +104,6 @@ YOUTH_STATIC_ASSERT(offsetof(FrameHeader, colorDataSize) == 20, "colorDataSize o
 YOUTH_STATIC_ASSERT(offsetof(FrameHeader, reserved) == 24, "reserved offset");
 YOUTH_STATIC_ASSERT(sizeof(MessageHeader) == 292, "MessageHeader must be 292 bytes");
 YOUTH_STATIC_ASSERT(MAX_MSG_SIZE - sizeof(MessageHeader) == 7900, "chunk payload is 7900 B");
+YOUTH_STATIC_ASSERT(sizeof(YouthPoseMsg) == 56, "YouthPoseMsg must be 56 bytes");
 
 #endif /* FRAME_DEFINITIONS_H */

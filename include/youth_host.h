@@ -43,6 +43,12 @@ int youth_chunk_count(size_t bytes);
 size_t youth_chunk_build(void* msg, int msg_type, int frame_id, uint32_t timestamp_ms, int width,
                          int height, const void* data, size_t data_bytes, int chunk);
 
+/* pose egress (MSG_TYPE_POSE): build / parse one message; build returns the message length,
+ * parse returns 1 when msg is a well-formed pose message */
+size_t youth_pose_msg_build(void* msg, int frame_id, uint32_t timestamp_ms, const float pose[12], uint32_t status,
+                            uint32_t inliers);
+int youth_pose_msg_parse(const void* msg, size_t len, int* frame_id, uint32_t* timestamp_ms, YouthPoseMsg* out);
+
 typedef struct youth_reasm youth_reasm;
 youth_reasm* youth_reasm_create(void);
 void youth_reasm_destroy(youth_reasm* r);

@@ -137,6 +137,9 @@ def host_lib():
         "youth_chunk_count": (C.c_int, [C.c_size_t]),
         "youth_chunk_build": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_void_p,
                                            C.c_size_t, C.c_int]),
+        "youth_pose_msg_build": (C.c_size_t, [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]),
+        "youth_pose_msg_parse": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_uint32),
+                                           C.c_void_p]),
         "youth_reasm_create": (C.c_void_p, []),
         "youth_reasm_destroy": (None, [C.c_void_p]),
         "youth_reasm_feed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),

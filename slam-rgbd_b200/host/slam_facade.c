@@ -15,6 +15,8 @@
  * No C++ exceptions exist here; errors are reported by return value and on stderr.
  */
 #define _GNU_SOURCE
+#include <fcntl.h>
+#include <mqueue.h>
 #include <pthread.h>
 #include <stdatomic.h>
 #include <stdio.h>
@@ -40,14 +42,16 @@ static struct {
   int qcap, head, count, busy; /* count = frames waiting; busy = claimed by the worker, slots still in use */
   int lossless, batch;
   pthread_t worker;
-  long accepted, dropped, tracked;
+  long accepted, dropped, tracked, poses_sent;
   atomic_int last_inliers;
+  mqd_t pose_mq; /* optional pose egress to the viewer queue (MSG_TYPE_POSE), -1 = off */
 } G = {.mu = PTHREAD_MUTEX_INITIALIZER,
        .nonempty = PTHREAD_COND_INITIALIZER,
        .nonfull = PTHREAD_COND_INITIALIZER,
        .idle = PTHREAD_COND_INITIALIZER,
        .lossless = -1,
-       .batch = -1};
+       .batch = -1,
+       .pose_mq = (mqd_t)-1};
 
 static size_t frame_px(void) { return (size_t)G.cfg.width * (size_t)G.cfg.height; }
 
@@ -74,8 +78,21 @@ static void* worker_main(void* arg) {
     if (!ok) fprintf(stderr, "AlgorithmModule: tracking failed: %s\n", youth_cuda_last_error());
     else atomic_store(&G.last_inliers, youth_cuda_last_inliers(G.h, 0));
 
+    long sent = 0;
+    if (ok && G.pose_mq != (mqd_t)-1) {
+      /* pose egress: one MSG_TYPE_POSE message per tracked frame on the
+       * logger->viewer queue; non-blocking, a full queue drops the pose rather than stalling tracking */
+      const int base = youth_cuda_frame_count(G.h, 0) - n;
+      const uint32_t inl = (uint32_t)atomic_load(&G.last_inliers);
+      char msg[sizeof(MessageHeader) + sizeof(YouthPoseMsg)];
+      for (int i = 0; i < n; ++i) {
+        const size_t len = youth_pose_msg_build(msg, base + i, G.ts[first + i], poses + 12 * (size_t)i, 0u, inl);
+        if (mq_send(G.pose_mq, msg, len, 0) == 0) ++sent;
+      }
+    }
     pthread_mutex_lock(&G.mu);
     G.busy = 0;
+    G.poses_sent += sent;
     G.tracked += ok ? n : 0;
     pthread_cond_broadcast(&G.nonfull);
     if (G.count == 0) pthread_cond_broadcast(&G.idle);
@@ -130,7 +147,20 @@ void initSlamModule(const char* config_file, const char* vocabulary_file) {
     return;
   }
   G.head = G.count = G.busy = 0;
-  G.accepted = G.dropped = G.tracked = 0;
+  G.accepted = G.dropped = G.tracked = G.poses_sent = 0;
+  G.pose_mq = (mqd_t)-1;
+  {
+    /* YOUTH_SLAM_POSE_MQ = queue name (e.g. /logger_viewer_queue): publish poses there */
+    const char* q = getenv("YOUTH_SLAM_POSE_MQ");
+    if (q && *q) {
+      struct mq_attr attr;
+      memset(&attr, 0, sizeof(attr));
+      attr.mq_maxmsg = 10; /* the reference's queue geometry, loggingModule.c:137-141 */
+      attr.mq_msgsize = MAX_MSG_SIZE;
+      G.pose_mq = mq_open(q, O_WRONLY | O_NONBLOCK | O_CREAT, 0644, &attr);
+      if (G.pose_mq == (mqd_t)-1) fprintf(stderr, "AlgorithmModule: cannot open pose queue %s (poses not published)\n", q);
+    }
+  }
   atomic_store(&G.last_inliers, 0);
   atomic_store(&G.stop_req, 0);
   if (pthread_create(&G.worker, NULL, worker_main, NULL) != 0) {
@@ -159,6 +189,10 @@ void stopSlamModule(void) {
   free(G.ts);
   G.ring = NULL;
   G.ts = NULL;
+  if (G.pose_mq != (mqd_t)-1) {
+    mq_close(G.pose_mq);
+    G.pose_mq = (mqd_t)-1;
+  }
 }
 
 int processSlamFrame(const int16_t* depth_data, const uint8_t* color_data, int width, int height, uint32_t timestamp) {

@@ -100,6 +100,35 @@ size_t youth_chunk_build(void* msg, int msg_type, int frame_id, uint32_t timesta
   return sizeof(h) + n;
 }
 
+size_t youth_pose_msg_build(void* msg, int frame_id, uint32_t timestamp_ms, const float pose[12], uint32_t status,
+                            uint32_t inliers) {
+  MessageHeader h;
+  YouthPoseMsg p;
+  memset(&h, 0, sizeof(h));
+  h.msgType = MSG_TYPE_POSE;
+  h.totalChunks = 1;
+  h.dataSize = (int)sizeof(p);
+  h.frameId = frame_id;
+  h.timestamp = timestamp_ms;
+  memcpy(p.pose, pose, sizeof(p.pose));
+  p.status = status;
+  p.inliers = inliers;
+  memcpy(msg, &h, sizeof(h));
+  memcpy((char*)msg + sizeof(h), &p, sizeof(p));
+  return sizeof(h) + sizeof(p);
+}
+
+int youth_pose_msg_parse(const void* msg, size_t len, int* frame_id, uint32_t* timestamp_ms, YouthPoseMsg* out) {
+  MessageHeader h;
+  if (!msg || !out || len < sizeof(h) + sizeof(*out)) return 0;
+  memcpy(&h, msg, sizeof(h));
+  if (h.msgType != MSG_TYPE_POSE || h.dataSize != (int)sizeof(*out)) return 0;
+  memcpy(out, (const char*)msg + sizeof(h), sizeof(*out));
+  if (frame_id) *frame_id = h.frameId;
+  if (timestamp_ms) *timestamp_ms = h.timestamp;
+  return 1;
+}
+
 struct youth_reasm {
   int width, height, frame_id;
   uint32_t timestamp;

@@ -222,3 +222,26 @@ def test_chunks_against_reference_sender(host, ref):
     d = np.ctypeslib.as_array(C.cast(host.youth_reasm_depth(r), C.POINTER(C.c_uint16)), shape=(480, 640))
     assert np.array_equal(d, depth[0])
     host.youth_reasm_destroy(r)
+
+
+def test_pose_message_roundtrip(host):
+    """pose egress to the viewer queue (SURVEY section 8(f) row 2): MSG_TYPE_POSE = 5, 292 + 56 bytes;
+    the frame reassembler ignores it like any unknown type."""
+    pose = np.arange(12, dtype=np.float32) * 0.25
+    msg = np.zeros(8192, dtype=np.uint8)
+    n = host.youth_pose_msg_build(msg.ctypes.data, 41, 1353, pose.ctypes.data, 2, 266000)
+    assert n == 292 + 56
+    hdr = MessageHeader.from_buffer_copy(msg[:292].tobytes())
+    assert (hdr.msgType, hdr.frameId, hdr.timestamp, hdr.dataSize, hdr.totalChunks) == (5, 41, 1353, 56, 1)
+    out = np.zeros(14, dtype=np.uint32)
+    fid, ts = C.c_int(), C.c_uint32()
+    assert host.youth_pose_msg_parse(msg.ctypes.data, n, C.byref(fid), C.byref(ts), out.ctypes.data) == 1
+    assert (fid.value, ts.value) == (41, 1353)
+    assert np.array_equal(out[:12].view(np.float32), pose) and out[12] == 2 and out[13] == 266000
+    assert host.youth_pose_msg_parse(msg.ctypes.data, n - 1, None, None, out.ctypes.data) == 0  # truncated
+    msg[0] = 2  # a depth chunk is not a pose message
+    assert host.youth_pose_msg_parse(msg.ctypes.data, n, None, None, out.ctypes.data) == 0
+    msg[0] = 5
+    r = host.youth_reasm_create()
+    assert host.youth_reasm_feed(r, msg.ctypes.data, n) == 0
+    host.youth_reasm_destroy(r)

@@ -148,6 +148,55 @@ def test_live_path_reference_chunks_to_tracker(pkg, small_seq):
     assert np.array_equal(poses.view(np.uint32), want.view(np.uint32))
 
 
+def test_pose_egress_to_viewer_queue(pkg, small_seq):
+    """(f)2: with YOUTH_SLAM_POSE_MQ set the facade publishes one MSG_TYPE_POSE message per tracked
+    frame on that POSIX queue; the messages carry the trajectory."""
+    class MqAttr(C.Structure):
+        _fields_ = [("mq_flags", C.c_long), ("mq_maxmsg", C.c_long), ("mq_msgsize", C.c_long), ("mq_curmsgs", C.c_long),
+                    ("pad", C.c_long * 4)]
+
+    rt = C.CDLL(None, use_errno=True)
+    rt.mq_open.restype = C.c_int
+    rt.mq_open.argtypes = [C.c_char_p, C.c_int, C.c_uint, C.POINTER(MqAttr)]
+    rt.mq_receive.restype = C.c_ssize_t
+    rt.mq_receive.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+    name = b"/youth_pose_mq_%d" % os.getpid()
+    attr = MqAttr(0, 10, 8192, 0)
+    rt.mq_unlink(name)
+    mq = rt.mq_open(name, os.O_RDONLY | os.O_CREAT | os.O_NONBLOCK, 0o644, C.byref(attr))
+    if mq < 0:
+        pytest.skip("POSIX message queues unavailable")
+    frames, _ = small_seq
+    host = pkg.host_lib()
+    os.environ["YOUTH_SLAM_POSE_MQ"] = name.decode()
+    try:
+        host.youthSlamSetOptions(1, 3)
+        host.initSlamModule(None, None)
+        assert host.isSlamModuleRunning() == 1
+        for i in range(6):
+            assert host.processSlamFrame(frames[i].ctypes.data, None, 640, 480, 33 * i) == 1
+        host.youthSlamDrain()
+        poses = np.empty((6, 12), dtype=np.float32)
+        assert host.youthSlamGetTrajectory(poses.ctypes.data, None, None, 6) == 6
+        host.stopSlamModule()
+    finally:
+        del os.environ["YOUTH_SLAM_POSE_MQ"]
+    buf = np.zeros(8192, dtype=np.uint8)
+    got = []
+    while True:
+        n = rt.mq_receive(mq, buf.ctypes.data, 8192, None)
+        if n < 0:
+            break
+        out = np.zeros(14, dtype=np.uint32)
+        fid, ts = C.c_int(), C.c_uint32()
+        assert host.youth_pose_msg_parse(buf.ctypes.data, n, C.byref(fid), C.byref(ts), out.ctypes.data) == 1
+        got.append((fid.value, ts.value, out[:12].view(np.float32).copy()))
+    rt.mq_close(mq)
+    rt.mq_unlink(name)
+    assert [g[0] for g in got] == list(range(6)) and [g[1] for g in got] == [33 * i for i in range(6)]
+    assert all(np.array_equal(g[2], poses[i]) for i, g in enumerate(got))
+
+
 def test_golden_fixture_through_cabi(pkg):
     from slam_rgbd_b200 import binding as B
 
