@@ -24,6 +24,8 @@
 
 #define YK_CHUNK_FRAMES 16 /* host-fed groups are copied + preprocessed in chunks of at least this many frames */
 #define YK_MAX_CHUNKS 64
+#define YK_GRAPH_MAX_N 8   /* groups of at most this many frames per stream run as one captured CUDA graph */
+#define YK_GRAPH_SLOTS (2 * YK_GRAPH_MAX_N)
 
 /* ------------------------------------------------------------------ errors */
 
@@ -85,12 +87,20 @@ struct youth_cuda_handle {
   float* traj;
   uint32_t* traj_status;
   int* last_inliers;
+  int* d_head;       /* device ring head (slot of the next frame) */
   int* h_count;      /* host mirror of seq_count */
   uint32_t* h_ts;    /* [S][cap] timestamps (host only) */
   long long total;   /* frames per stream since init / full reset (ring position) */
   int32_t* corr_dbg; /* debug correspondence map (level-0 sized) */
   cudaEvent_t t0, t1;
   uint64_t launches;
+  /* CUDA graphs of the whole kernel schedule for small host-fed groups (launch-bound live path) */
+  struct {
+    cudaGraphExec_t exec;
+    int n, k;
+    uint64_t launches; /* kernels inside the graph */
+  } graphs[YK_GRAPH_SLOTS];
+  bool graphs_enabled;
   /* per-kernel-class event timing (youth_cuda_profile_*): off on the normal path */
   bool prof_on;
   cudaEvent_t* prof_ev; /* pairs: [2*i] before, [2*i+1] after launch i */
@@ -216,6 +226,9 @@ extern "C" void youth_cuda_destroy(youth_cuda_handle* h) {
   cudaFree(h->traj);
   cudaFree(h->traj_status);
   cudaFree(h->last_inliers);
+  cudaFree(h->d_head);
+  for (int g2 = 0; g2 < YK_GRAPH_SLOTS; ++g2)
+    if (h->graphs[g2].exec) cudaGraphExecDestroy(h->graphs[g2].exec);
   cudaFree(h->corr_dbg);
   if (h->prof_ev) {
     for (int i = 0; i < 2 * h->prof_cap; ++i) cudaEventDestroy(h->prof_ev[i]);
@@ -319,10 +332,15 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
   CU(dalloc(&h->traj, (size_t)h->S * cfg->traj_capacity * 12));
   CU(dalloc(&h->traj_status, (size_t)h->S * cfg->traj_capacity));
   CU(dalloc(&h->last_inliers, (size_t)h->S));
+  CU(dalloc(&h->d_head, (size_t)1));
   CU(dalloc(&h->corr_dbg, frame_px));
   h->h_count = (int*)calloc(h->S, sizeof(int));
   h->h_ts = (uint32_t*)calloc((size_t)h->S * cfg->traj_capacity, sizeof(uint32_t));
   if (!h->h_count || !h->h_ts) return fail("host allocation failed");
+  {
+    const char* g = getenv("YOUTH_CUDA_GRAPHS");
+    h->graphs_enabled = !(g && *g == '0');
+  }
   CU(cudaEventCreate(&h->t0));
   CU(cudaEventCreate(&h->t1));
   CU(cudaDeviceSynchronize());
@@ -351,7 +369,7 @@ extern "C" int youth_cuda_init(const youth_cuda_config* cfg, youth_cuda_handle**
 static RingGeom ring_of(const youth_cuda_handle* h, int n) {
   RingGeom r;
   r.n = n;
-  r.head = (int)(h->total % h->R);
+  r.head = h->d_head; /* == total % R, kept on the device */
   r.R = h->R;
   r.S = h->S;
   return r;
@@ -481,6 +499,7 @@ static int enqueue_icp(youth_cuda_handle* h, int n) {
     cp.traj = h->traj;
     cp.traj_status = h->traj_status;
     cp.last_inliers = h->last_inliers;
+    cp.head = h->d_head;
     cp.cap = c.traj_capacity;
     ProfScope ps(h, YOUTH_PROF_MISC);
     k_compose<<<h->S, 128, 0, h->stream>>>(cp);
@@ -515,29 +534,66 @@ extern "C" int youth_cuda_track_batch(youth_cuda_handle* h, const uint16_t* cons
         CU(cudaEventSynchronize(h->raw_free[k])); /* the pinned staging copy is about to be overwritten */
       CU(cudaStreamWaitEvent(h->copy_stream, h->raw_free[k], 0));
     }
-    /* copy and preprocess in chunks: the H2D of chunk c+1 overlaps ingest of chunk c */
-    int ch = (n_frames + YK_MAX_CHUNKS - 1) / YK_MAX_CHUNKS;
-    if (ch < YK_CHUNK_FRAMES) ch = YK_CHUNK_FRAMES;
-    for (int s = 0; s < h->S; ++s) dev_ptrs[s] = h->raw[k] + (size_t)s * n_frames * frame_px;
-    int ci = 0;
-    for (int f0 = 0; f0 < n_frames; f0 += ch, ++ci) {
-      const int cn = n_frames - f0 < ch ? n_frames - f0 : ch;
-      const size_t off = (size_t)f0 * frame_px, bytes = (size_t)cn * frame_px * sizeof(uint16_t);
+    if (h->graphs_enabled && !h->prof_on && n_frames <= YK_GRAPH_MAX_N) {
+      /* launch-bound small group: one H2D per stream on the compute stream, then the whole kernel
+       * schedule as ONE captured graph (valid from call to call: ring head and counters live on the device) */
       for (int s = 0; s < h->S; ++s) {
-        uint16_t* dst = h->raw[k] + (size_t)s * n_frames * frame_px + off;
-        const uint16_t* src = depth[s] + off;
+        uint16_t* dst = h->raw[k] + (size_t)s * n_frames * frame_px;
+        const uint16_t* src = depth[s];
         if (mem_kind == YOUTH_MEM_HOST) {
-          uint16_t* stage = h->pinned[k] + (size_t)s * n_frames * frame_px + off;
-          memcpy(stage, src, bytes); /* synchronous copy: the caller may reuse its buffer (SLAM.cpp:133-134) */
+          uint16_t* stage = h->pinned[k] + (size_t)s * n_frames * frame_px;
+          memcpy(stage, src, seq_bytes);
           src = stage;
         }
-        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        CU(cudaMemcpyAsync(dst, src, seq_bytes, cudaMemcpyHostToDevice, h->stream));
+        dev_ptrs[s] = dst;
       }
-      CU(cudaEventRecord(h->chunk_ready[k][ci], h->copy_stream));
-      CU(cudaStreamWaitEvent(h->stream, h->chunk_ready[k][ci], 0));
-      if (!enqueue_preprocess(h, dev_ptrs, n_frames, f0, cn)) return 0;
+      const int gi = (n_frames - 1) * 2 + k;
+      if (!h->graphs[gi].exec) {
+        cudaGraph_t graph = NULL;
+        const uint64_t before = h->launches;
+        CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int ok = enqueue_preprocess(h, dev_ptrs, n_frames, 0, n_frames) && enqueue_icp(h, n_frames);
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        if (!ok || ce != cudaSuccess || !graph) {
+          if (graph) cudaGraphDestroy(graph);
+          return fail("CUDA graph capture failed: %s", ce != cudaSuccess ? cudaGetErrorString(ce) : youth_cuda_last_error());
+        }
+        h->graphs[gi].launches = h->launches - before;
+        h->launches = before;
+        ce = cudaGraphInstantiate(&h->graphs[gi].exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+        h->graphs[gi].n = n_frames;
+        h->graphs[gi].k = k;
+      }
+      CU(cudaGraphLaunch(h->graphs[gi].exec, h->stream));
+      h->launches += h->graphs[gi].launches;
+    } else {
+      /* copy and preprocess in chunks: the H2D of chunk c+1 overlaps ingest of chunk c */
+      int ch = (n_frames + YK_MAX_CHUNKS - 1) / YK_MAX_CHUNKS;
+      if (ch < YK_CHUNK_FRAMES) ch = YK_CHUNK_FRAMES;
+      for (int s = 0; s < h->S; ++s) dev_ptrs[s] = h->raw[k] + (size_t)s * n_frames * frame_px;
+      int ci = 0;
+      for (int f0 = 0; f0 < n_frames; f0 += ch, ++ci) {
+        const int cn = n_frames - f0 < ch ? n_frames - f0 : ch;
+        const size_t off = (size_t)f0 * frame_px, bytes = (size_t)cn * frame_px * sizeof(uint16_t);
+        for (int s = 0; s < h->S; ++s) {
+          uint16_t* dst = h->raw[k] + (size_t)s * n_frames * frame_px + off;
+          const uint16_t* src = depth[s] + off;
+          if (mem_kind == YOUTH_MEM_HOST) {
+            uint16_t* stage = h->pinned[k] + (size_t)s * n_frames * frame_px + off;
+            memcpy(stage, src, bytes); /* synchronous copy: the caller may reuse its buffer (SLAM.cpp:133-134) */
+            src = stage;
+          }
+          CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        }
+        CU(cudaEventRecord(h->chunk_ready[k][ci], h->copy_stream));
+        CU(cudaStreamWaitEvent(h->stream, h->chunk_ready[k][ci], 0));
+        if (!enqueue_preprocess(h, dev_ptrs, n_frames, f0, cn)) return 0;
+      }
+      if (!enqueue_icp(h, n_frames)) return 0;
     }
-    if (!enqueue_icp(h, n_frames)) return 0;
     CU(cudaEventRecord(h->raw_free[k], h->stream));
     h->raw_used[k] = true;
   } else {
@@ -584,6 +640,7 @@ extern "C" int youth_cuda_reset(youth_cuda_handle* h, int stream) {
   if (stream < 0) {
     CU(cudaMemsetAsync(h->seq_count, 0, sizeof(int) * h->S, h->stream));
     CU(cudaMemsetAsync(h->last_inliers, 0, sizeof(int) * h->S, h->stream));
+    CU(cudaMemsetAsync(h->d_head, 0, sizeof(int), h->stream));
     memset(h->h_count, 0, sizeof(int) * h->S);
     h->total = 0; /* stream-ordered: later groups see the cleared counters */
   } else {
