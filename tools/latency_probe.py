@@ -33,3 +33,15 @@ for ppt in (64, 16):
           f"pinned enqueue-only {run(B.MEM_HOST_PINNED, pin, False):7.1f} | pageable blocking "
           f"{run(B.MEM_HOST, frames.ctypes.data, True):7.1f}")
     trk.close()
+
+# per-kernel-class device time for single-frame groups (CUDA events around every launch)
+trk = B.Tracker(pkg.default_config(batch=1, traj_capacity=100000))
+for i in range(8):
+    trk.track_batch_ptrs([dev.data_ptr() + i * fb], 1, B.MEM_DEVICE)
+trk.profile(True)
+for i in range(50):
+    trk.track_batch_ptrs([dev.data_ptr() + (8 + i) * fb], 1, B.MEM_DEVICE)
+ms, n = trk.profile_read()
+names = ["k_ingest", "k_normals", "k_icp_L0", "k_icp_L1", "k_icp_L2", "k_icp_L3", "-", "k_compose"]
+print("batch-1 per-launch device time (us):", {names[i]: round(ms[i] / n[i] * 1e3, 1) for i in range(8) if n[i]})
+trk.close()
