@@ -189,3 +189,44 @@ def test_edge_cases(pkg, oracle):
     assert trk.frame_count() == 0
     assert np.array_equal(trk.track_batch([empty[:1]])[0][0], ident)
     trk.close()
+
+
+RANDOM_CONFIGS = [
+    # width, height, levels, extra config, noise
+    (96, 64, 1, dict(iters=[6, 0, 0, 0], sigma_range_mm=10.0, sigma_space_px=2.0), 0),
+    (128, 96, 2, dict(iters=[5, 3, 0, 0], depth_factor=5000.0, depth_max_mm=40000, bilateral=0), 1),
+    (200, 152, 3, dict(iters=[4, 3, 2, 0], dist_thresh_m=0.03, cos_thresh=0.98, icp_ppt=2), 1),
+    (320, 240, 4, dict(iters=[3, 2, 2, 2], sigma_range_mm=60.0, icp_ppt=128, depth_min_mm=700), 0),
+    (72, 40, 2, dict(iters=[4, 4, 0, 0], min_inliers=100000), 0),  # never enough inliers: every pair flagged lost
+    (640, 480, 3, dict(iters=[2, 1, 1, 0], fx=525.0, fy=531.5, cx=311.25, cy=247.75, icp_ppt=32), 1),
+]
+
+
+@pytest.mark.parametrize("w,h,levels,extra,noise", RANDOM_CONFIGS)
+def test_parity_across_configurations(pkg, oracle, w, h, levels, extra, noise):
+    """sizes with partial ingest tiles, 1-4 levels, other intrinsics / depth scales / gates /
+    reduction geometries: depth pyramid, masks, maps, poses and status all bit-identical."""
+    from slam_rgbd_b200 import binding as B
+
+    scale = w / 640.0
+    base = dict(width=w, height=h, levels=levels, fx=570.3 * scale, fy=570.3 * scale, cx=w / 2.0, cy=h / 2.0, batch=3)
+    base.update(extra)
+    frames = pkg.synth_sequence(3, w, h, sequence=7, noise=noise)
+    if base.get("depth_factor", 1000.0) != 1000.0:
+        frames = (frames.astype(np.uint32) * 5).astype(np.uint16)  # 0.2 mm units
+    trk = make_tracker(pkg, **base)
+    ocfg = oracle.config_from(trk.cfg)
+    poses = trk.track_batch([frames])[0]
+    want, st_o, _ = oracle.track_sequence(ocfg, frames)
+    _, _, st = trk.trajectory()
+    assert np.array_equal(st, st_o)
+    assert np.array_equal(poses.view(np.uint32), want.view(np.uint32))
+    of = oracle.OFrame(ocfg, frames[2])
+    for level in range(levels):
+        assert np.array_equal(trk.debug_read(B.DBG_DEPTH, 2, level), of.depth(level))
+        assert np.array_equal(trk.debug_read(B.DBG_MASK, 2, level), of.mask(level))
+        assert np.array_equal(trk.debug_read(B.DBG_VERTEX, 2, level).view(np.uint32), of.vmap(level).view(np.uint32))
+        assert np.array_equal(trk.debug_read(B.DBG_NORMAL, 2, level).view(np.uint32), of.nmap(level).view(np.uint32))
+    if extra.get("min_inliers", 0) > 50000:
+        assert list(st) == [1, 2, 2]
+    trk.close()
