@@ -19,6 +19,11 @@
  * youth_cuda_last_error() returns a thread-local description of the last failure.
  * There is no CPU fallback: without a CUDA device every compute entry point fails.
  *
+ * Threading: a handle is not thread-safe -- drive each handle from one thread (the facade's
+ * worker does) or lock around it; different handles (e.g. one per GPU) are independent.
+ * Groups of at most 8 frames per sequence fed from host memory run as one captured CUDA graph
+ * (the launch-bound live path); YOUTH_CUDA_GRAPHS=0 in the environment disables that.
+ *
  * Numerical contract (frozen by oracle/youth_oracle.c): fused
  * multiply-add only where the specification names it (stage 3), never by compiler
  * contraction; IEEE division/sqrt; fixed-order reductions -- the device results are
