@@ -40,8 +40,8 @@ class Frame(C.Structure):
 
 def build(force=False):
     so = os.path.join(HERE, "_build", "libyouth_oracle_hwfma.so")
-    src = os.path.join(HERE, "youth_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(HERE, f) for f in ("youth_oracle.c", "youth_codec_oracle.c", "youth_oracle.h")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         subprocess.run(["make", "-C", HERE, "all"], check=True, capture_output=True)
     return so
 
@@ -91,6 +91,12 @@ def lib(fast=False):
         "yo_compose": (None, [C.c_void_p, C.c_void_p, C.c_void_p]),
         "yo_track_sequence": (C.c_double, [CP, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     }
+    if not fast:  # the codec statement lives in the parity builds only
+        sig.update({
+            "yc_max_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+            "yc_encode": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+            "yc_decode": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]),
+        })
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
         fn.restype = res
@@ -196,3 +202,19 @@ def track_sequence(cfg, frames, fast=False):
     status = np.empty(n, dtype=np.uint32)
     secs = lib(fast).yo_track_sequence(C.byref(cfg), frames.ctypes.data, n, poses.ctypes.data, status.ctypes.data)
     return poses, status, secs
+
+
+def codec_encode(frame):
+    """uint16 [H][W] -> packed bytes (numpy uint8) with the CPU statement of the YD16 codec."""
+    assert frame.dtype == np.uint16 and frame.flags.c_contiguous
+    h, w = frame.shape
+    out = np.zeros(lib().yc_max_bytes(w, h), dtype=np.uint8)
+    n = lib().yc_encode(frame.ctypes.data, w, h, out.ctypes.data)
+    return out[:n].copy()
+
+
+def codec_decode(stream, w, h):
+    stream = np.ascontiguousarray(stream, dtype=np.uint8)
+    out = np.empty((h, w), dtype=np.uint16)
+    ok = lib().yc_decode(stream.ctypes.data, stream.size, w, h, out.ctypes.data)
+    return out if ok else None

@@ -5,6 +5,7 @@ This Python package is only the ctypes view of those libraries used by tests, be
 and the multi-GPU launcher; it contains no arithmetic of its own and no CPU fallback.
 """
 from .binding import (  # noqa: F401
+    Codec,
     CudaLibraryMissing,
     SynthConfig,
     Tracker,

@@ -105,6 +105,15 @@ def cuda_lib():
         "youth_cuda_profile_read": (C.c_int, [H, C.c_void_p, C.c_void_p]),
         "youth_cuda_last_error": (C.c_char_p, []),
         "youth_cuda_abi_version": (C.c_int, []),
+        # include/youth_codec.h
+        "youth_codec_max_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+        "youth_codec_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(H)]),
+        "youth_codec_destroy": (None, [H]),
+        "youth_codec_encode": (C.c_int, [H, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+        "youth_codec_decode": (C.c_int, [H, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+        "youth_codec_last_kernel_ms": (C.c_float, [H]),
+        "youth_codec_launch_count": (C.c_uint64, [H]),
+        "youth_cuda_track_batch_packed": (C.c_int, [H, u16pp, u16pp, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError = header/library drift: fail loudly
@@ -257,6 +266,16 @@ class Tracker:
         self.track_batch_ptrs([f.ctypes.data for f in frames], n, MEM_HOST, None, poses)
         return poses
 
+    def track_batch_packed(self, streams, offsets, n, mem_kind=MEM_HOST, ts=None, want_poses=True):
+        """streams / offsets: one uint8 array and one uint64 [n+1] array per sequence (YD16, back to back)."""
+        sp = (C.c_void_p * len(streams))(*[a.ctypes.data for a in streams])
+        op = (C.c_void_p * len(offsets))(*[a.ctypes.data for a in offsets])
+        poses = np.empty((len(streams), n, 12), dtype=np.float32) if want_poses else None
+        self._check(self.lib.youth_cuda_track_batch_packed(
+            self.h, sp, op, n, mem_kind, ts.ctypes.data if ts is not None else None,
+            poses.ctypes.data if want_poses else None), "youth_cuda_track_batch_packed")
+        return poses
+
     def sync(self):
         self._check(self.lib.youth_cuda_sync(self.h), "youth_cuda_sync")
 
@@ -319,3 +338,58 @@ class Tracker:
 
     def launch_count(self):
         return int(self.lib.youth_cuda_launch_count(self.h))
+
+
+class Codec:
+    """Thin object view of a ``youth_codec`` (include/youth_codec.h): the YD16 lossless depth codec."""
+
+    def __init__(self, width, height, max_frames=1, device=0):
+        self.lib = cuda_lib()
+        self.w, self.h_, self.max_frames = width, height, max_frames
+        self.h = C.c_void_p()
+        if not self.lib.youth_codec_create(width, height, max_frames, device, C.byref(self.h)):
+            raise RuntimeError("youth_codec_create failed: " + self.lib.youth_cuda_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.lib.youth_codec_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def max_bytes(self):
+        return self.lib.youth_codec_max_bytes(self.w, self.h_)
+
+    def encode_ptr(self, ptr, n, mem_kind, out=None):
+        """-> (packed uint8 array holding the n streams back to back, uint64 offsets [n+1])"""
+        if out is None:
+            out = np.empty(n * self.max_bytes(), dtype=np.uint8)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        if not self.lib.youth_codec_encode(self.h, ptr, mem_kind, n, out.ctypes.data, out.nbytes, offs.ctypes.data):
+            raise RuntimeError("youth_codec_encode failed: " + self.lib.youth_cuda_last_error().decode())
+        return out[:int(offs[n])], offs
+
+    def encode(self, frames):
+        assert frames.dtype == np.uint16 and frames.flags.c_contiguous and frames.shape[1:] == (self.h_, self.w)
+        return self.encode_ptr(frames.ctypes.data, frames.shape[0], MEM_HOST)
+
+    def decode(self, packed, offs):
+        n = len(offs) - 1
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        out = np.empty((n, self.h_, self.w), dtype=np.uint16)
+        if not self.lib.youth_codec_decode(self.h, packed.ctypes.data, offs.ctypes.data, n, out.ctypes.data, MEM_HOST):
+            raise RuntimeError("youth_codec_decode failed: " + self.lib.youth_cuda_last_error().decode())
+        return out
+
+    def decode_to_device(self, packed, offs, dev_ptr):
+        n = len(offs) - 1
+        if not self.lib.youth_codec_decode(self.h, packed.ctypes.data, offs.ctypes.data, n, dev_ptr, MEM_DEVICE):
+            raise RuntimeError("youth_codec_decode failed: " + self.lib.youth_cuda_last_error().decode())
+
+    def last_kernel_ms(self):
+        return float(self.lib.youth_codec_last_kernel_ms(self.h))

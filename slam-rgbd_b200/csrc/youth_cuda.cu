@@ -20,6 +20,7 @@
 #include <string.h>
 
 #include "youth_cuda.h"
+#include "youth_codec.h"
 #include "youth_kernels.cuh"
 
 #define YK_CHUNK_FRAMES 16 /* host-fed groups are copied + preprocessed in chunks of at least this many frames */
@@ -108,6 +109,12 @@ struct youth_cuda_handle {
   int prof_n, prof_cap;
   double prof_ms[YOUTH_PROF_CLASSES];
   uint64_t prof_launches[YOUTH_PROF_CLASSES];
+  /* packed (YD16) input path, created on first use (youth_cuda_track_batch_packed) */
+  struct youth_codec* codec;
+  unsigned long long* pk_h_off[2]; /* pinned: device offsets of the group's streams */
+  unsigned long long* pk_d_off[2];
+  cudaEvent_t pk_free;             /* the group's last decode has read the packed bytes */
+  bool pk_used;
 };
 
 /* bracket one launch with events when profiling is on */
@@ -197,6 +204,8 @@ static cudaError_t dalloc(T** p, size_t count) {
   return e;
 }
 
+#include "youth_codec.cuh"
+
 extern "C" void youth_cuda_destroy(youth_cuda_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
@@ -230,6 +239,12 @@ extern "C" void youth_cuda_destroy(youth_cuda_handle* h) {
   for (int g2 = 0; g2 < YK_GRAPH_SLOTS; ++g2)
     if (h->graphs[g2].exec) cudaGraphExecDestroy(h->graphs[g2].exec);
   cudaFree(h->corr_dbg);
+  if (h->codec) youth_codec_destroy(h->codec);
+  for (int k = 0; k < 2; ++k) {
+    if (h->pk_h_off[k]) cudaFreeHost(h->pk_h_off[k]);
+    cudaFree(h->pk_d_off[k]);
+  }
+  if (h->pk_free) cudaEventDestroy(h->pk_free);
   if (h->prof_ev) {
     for (int i = 0; i < 2 * h->prof_cap; ++i) cudaEventDestroy(h->prof_ev[i]);
     free(h->prof_ev);
@@ -509,6 +524,26 @@ static int enqueue_icp(youth_cuda_handle* h, int n) {
   return 1;
 }
 
+/* host bookkeeping of a group that has been enqueued, and the optional blocking pose read-back */
+static int finish_group(youth_cuda_handle* h, int n_frames, const uint32_t* timestamps_ms, float* poses_out) {
+  for (int s = 0; s < h->S; ++s) {
+    for (int i = 0; i < n_frames; ++i)
+      h->h_ts[(size_t)s * h->cfg.traj_capacity + h->h_count[s] + i] =
+          timestamps_ms ? timestamps_ms[i] : (uint32_t)(((long long)(h->h_count[s] + i) * 100) / 3);
+    h->h_count[s] += n_frames;
+  }
+  h->total += n_frames;
+  if (poses_out) {
+    for (int s = 0; s < h->S; ++s) {
+      const float* src = h->traj + ((size_t)s * h->cfg.traj_capacity + (h->h_count[s] - n_frames)) * 12;
+      CU(cudaMemcpyAsync(poses_out + (size_t)s * n_frames * 12, src, sizeof(float) * 12 * n_frames,
+                         cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  return 1;
+}
+
 extern "C" int youth_cuda_track_batch(youth_cuda_handle* h, const uint16_t* const* depth, int n_frames,
                                       int mem_kind, const uint32_t* timestamps_ms, float* poses_out) {
   if (!h || !depth) return fail("null argument");
@@ -599,21 +634,86 @@ extern "C" int youth_cuda_track_batch(youth_cuda_handle* h, const uint16_t* cons
   } else {
     return fail("unknown mem_kind %d", mem_kind);
   }
+  return finish_group(h, n_frames, timestamps_ms, poses_out);
+}
+
+/* A group whose frames arrive as YD16 streams: the packed bytes cross PCIe (about a third of the raw
+ * frames), k_yd16_decode unpacks them straight into the raw landing zone, then the normal schedule.
+ * Chunked like the raw host path: the H2D of chunk c+1 overlaps decode + ingest of chunk c. */
+extern "C" int youth_cuda_track_batch_packed(youth_cuda_handle* h, const uint8_t* const* streams,
+                                             const uint64_t* const* offsets, int n_frames, int mem_kind,
+                                             const uint32_t* timestamps_ms, float* poses_out) {
+  if (!h || !streams || !offsets) return fail("null argument");
+  if (n_frames < 1 || n_frames > h->B) return fail("n_frames must be 1..batch (%d)", h->B);
+  if (mem_kind != YOUTH_MEM_HOST && mem_kind != YOUTH_MEM_HOST_PINNED) return fail("packed input must be host memory");
   for (int s = 0; s < h->S; ++s) {
-    for (int i = 0; i < n_frames; ++i)
-      h->h_ts[(size_t)s * h->cfg.traj_capacity + h->h_count[s] + i] =
-          timestamps_ms ? timestamps_ms[i] : (uint32_t)(((long long)(h->h_count[s] + i) * 100) / 3);
-    h->h_count[s] += n_frames;
+    if (!streams[s] || !offsets[s]) return fail("streams[%d] / offsets[%d] is NULL", s, s);
+    if (h->h_count[s] + n_frames > h->cfg.traj_capacity) return fail("trajectory capacity (%d) exceeded", h->cfg.traj_capacity);
   }
-  h->total += n_frames;
-  if (poses_out) {
-    for (int s = 0; s < h->S; ++s) {
-      const float* src = h->traj + ((size_t)s * h->cfg.traj_capacity + (h->h_count[s] - n_frames)) * 12;
-      CU(cudaMemcpyAsync(poses_out + (size_t)s * n_frames * 12, src, sizeof(float) * 12 * n_frames,
-                         cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaSetDevice(h->cfg.device));
+  if (!h->codec) {
+    if (!youth_codec_create(h->cfg.width, h->cfg.height, h->P, h->cfg.device, &h->codec)) return 0;
+    for (int k = 0; k < 2; ++k) {
+      CU(cudaHostAlloc((void**)&h->pk_h_off[k], sizeof(unsigned long long) * ((size_t)h->P + 1), cudaHostAllocDefault));
+      CU(dalloc(&h->pk_d_off[k], (size_t)h->P + 1));
     }
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaEventCreateWithFlags(&h->pk_free, cudaEventDisableTiming));
   }
+  youth_codec* c = h->codec;
+  for (int s = 0; s < h->S; ++s)
+    for (int i = 0; i < n_frames; ++i) {
+      if (offsets[s][i + 1] < offsets[s][i]) return fail("offsets must be non-decreasing");
+      if (!codec_check_header(c, streams[s] + offsets[s][i], offsets[s][i + 1] - offsets[s][i], s * n_frames + i)) return 0;
+    }
+  const int k = h->raw_turn;
+  h->raw_turn ^= 1;
+  if (h->raw_used[k]) CU(cudaEventSynchronize(h->raw_free[k])); /* pk_h_off[k] and raw[k] of two calls ago are free */
+  if (h->pk_used) CU(cudaStreamWaitEvent(h->copy_stream, h->pk_free, 0)); /* d_packed of the previous group was read */
+  /* device placement of the streams: sequence after sequence, byte granular */
+  unsigned long long* O = h->pk_h_off[k];
+  unsigned long long base = 0;
+  for (int s = 0; s < h->S; ++s) {
+    for (int i = 0; i < n_frames; ++i) O[(size_t)s * n_frames + i] = base + (offsets[s][i] - offsets[s][0]);
+    base += offsets[s][n_frames] - offsets[s][0];
+  }
+  O[(size_t)h->S * n_frames] = base;
+  if (base > (unsigned long long)h->P * c->stride) return fail("packed group larger than the context");
+  CU(cudaMemcpyAsync(h->pk_d_off[k], O, sizeof(unsigned long long) * ((size_t)h->S * n_frames + 1), cudaMemcpyHostToDevice,
+                     h->copy_stream));
+  CU(cudaMemsetAsync(c->d_err, 0, sizeof(unsigned int), h->copy_stream));
+  const size_t frame_px = (size_t)h->cfg.width * h->cfg.height;
+  const uint16_t* dev_ptrs[YK_MAX_STREAMS];
+  for (int s = 0; s < h->S; ++s) dev_ptrs[s] = h->raw[k] + (size_t)s * n_frames * frame_px;
+  int ch = (n_frames + YK_MAX_CHUNKS - 1) / YK_MAX_CHUNKS;
+  if (ch < YK_CHUNK_FRAMES) ch = YK_CHUNK_FRAMES;
+  int ci = 0;
+  for (int f0 = 0; f0 < n_frames; f0 += ch, ++ci) {
+    const int cn = n_frames - f0 < ch ? n_frames - f0 : ch;
+    for (int s = 0; s < h->S; ++s) {
+      const size_t j0 = (size_t)s * n_frames + f0;
+      CU(cudaMemcpyAsync(c->d_packed + O[j0], streams[s] + offsets[s][f0], (size_t)(O[j0 + cn] - O[j0]),
+                         cudaMemcpyHostToDevice, h->copy_stream));
+    }
+    CU(cudaEventRecord(h->chunk_ready[k][ci], h->copy_stream));
+    CU(cudaStreamWaitEvent(h->stream, h->chunk_ready[k][ci], 0));
+    for (int s = 0; s < h->S; ++s) {
+      const size_t j0 = (size_t)s * n_frames + f0;
+      ProfScope ps(h, YOUTH_PROF_MISC);
+      h->launches++; /* two kernels per decode */
+      if (!codec_enqueue_decode(c, h->stream, c->d_packed, h->pk_d_off[k] + j0, c->d_tile_sum + j0 * c->tiles, cn,
+                                h->raw[k] + j0 * frame_px))
+        return 0;
+    }
+    if (!enqueue_preprocess(h, dev_ptrs, n_frames, f0, cn)) return 0;
+  }
+  CU(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaEventRecord(h->pk_free, h->stream));
+  h->pk_used = true;
+  if (!enqueue_icp(h, n_frames)) return 0;
+  CU(cudaEventRecord(h->raw_free[k], h->stream));
+  h->raw_used[k] = true;
+  if (!finish_group(h, n_frames, timestamps_ms, poses_out)) return 0;
+  if (poses_out && *c->h_err) return fail("malformed YD16 stream (device check 0x%x); reset the tracker", *c->h_err);
   return 1;
 }
 
@@ -630,6 +730,11 @@ extern "C" int youth_cuda_sync(youth_cuda_handle* h) {
   CU(cudaSetDevice(h->cfg.device));
   CU(cudaStreamSynchronize(h->copy_stream));
   CU(cudaStreamSynchronize(h->stream));
+  if (h->codec && *h->codec->h_err) {
+    const unsigned int e = *h->codec->h_err;
+    *h->codec->h_err = 0;
+    return fail("malformed YD16 stream in an earlier packed group (device check 0x%x); reset the tracker", e);
+  }
   return 1;
 }
 
