@@ -354,6 +354,63 @@ def run_ours(args):
     poses_e2e = host_traj[0].copy()
     e2e_matches = bool(np.array_equal(poses_e2e.view(np.uint32), poses.view(np.uint32)))
 
+    # ---- packed-input arm: the same step fed from YD16 streams (include/youth_codec.h) in pinned host
+    # memory; the packed bytes cross PCIe and are unpacked on the device.  Reported next to e2e.
+    packed_info = None
+    if not args.no_packed:
+        cd = pkg.Codec(Wd, Hd, max_frames=FRAMES, device=local)
+        enc = [cd.encode_ptr(d_base + k * seq_bytes, FRAMES, B.MEM_DEVICE) for k in range(S)]
+        enc_ms = cd.last_kernel_ms()
+        back = torch.empty(FRAMES * Wd * Hd, dtype=torch.int16, device=f"cuda:{local}")
+        cd.decode_to_device(enc[0][0], enc[0][1], back.data_ptr())
+        dec_ms = cd.last_kernel_ms()
+        codec_ok = bool(torch.equal(back.view(FRAMES, Hd, Wd), d_frames[0]))
+        del back
+        cd.close()
+        pk_bytes = [int(e[1][-1]) for e in enc]
+        pk_pin = [trk.lib.youth_cuda_host_alloc(b) for b in pk_bytes]
+        for ptr, e in zip(pk_pin, enc):
+            C.memmove(ptr, e[0].ctypes.data, len(e[0]))
+        pk_ptrs = (C.c_void_p * S)(*pk_pin)
+
+        def step_packed():
+            trk.reset()
+            for a, n in groups:
+                offs = [np.ascontiguousarray(e[1][a:a + n + 1]) for e in enc]
+                op = (C.c_void_p * S)(*[o.ctypes.data for o in offs])
+                ok = trk.lib.youth_cuda_track_batch_packed(trk.h, pk_ptrs, op, n, B.MEM_HOST_PINNED, None, None)
+                assert ok, trk.lib.youth_cuda_last_error()
+            for k in range(S):
+                got = trk.lib.youth_cuda_get_trajectory(trk.h, k, 0, FRAMES, host_traj[k].ctypes.data, None, None)
+                assert got == FRAMES
+
+        for _ in range(args.warmup):
+            step_packed()
+        barrier()
+        psteps = max(1, min(args.steps, 20))
+        t0 = time.perf_counter()
+        for _ in range(psteps):
+            step_packed()
+        trk.sync()
+        pk_s = time.perf_counter() - t0
+        if dist is not None:
+            torch.cuda.synchronize()
+            t = torch.tensor([pk_s], device=f"cuda:{local}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pk_s = float(t.item())
+        raw_b = FRAMES * frame_bytes
+        packed_info = {
+            "e2e_value": world * S * FRAMES * psteps / pk_s, "unit": "frames/s", "steps": psteps,
+            "h2d_bytes_per_step": int(sum(pk_bytes)), "compression_ratio": S * raw_b / float(sum(pk_bytes)),
+            "bit_identical_to_device_arm": bool(np.array_equal(host_traj[0].view(np.uint32), poses.view(np.uint32))),
+            "codec_round_trip_identical": codec_ok,
+            "k_yd16_encode": {"ms_per_300_frames": enc_ms, "gbs": (raw_b + pk_bytes[-1]) / (enc_ms * 1e-3) / 1e9},
+            "k_yd16_decode": {"ms_per_300_frames": dec_ms, "gbs": (raw_b + pk_bytes[0]) / (dec_ms * 1e-3) / 1e9},
+            "what": "youth_cuda_track_batch_packed: YD16 streams in pinned host memory, unpacked on the device",
+        }
+        for ptr in pk_pin:
+            trk.lib.youth_cuda_host_free(ptr)
+
     # ---- per-kernel timing (separate profiled step: events around every launch)
     trk.profile(True)
     step_device()
@@ -446,6 +503,7 @@ def run_ours(args):
                                        "frames_flagged_lost": lost},
         "frames_per_sec_per_gpu": value / world,
         "streaming_single_frame": streaming,
+        "packed_input": packed_info,
     }
     print(json.dumps(line), flush=True)
     C.cast(pin_ptr, C.c_void_p)
@@ -468,6 +526,7 @@ def main():
     ap.add_argument("--width", type=int, default=W)
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--levels", type=int, default=3)
+    ap.add_argument("--no-packed", action="store_true", help="skip the YD16 packed-input arm")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -20,6 +20,7 @@
 #include <stdio.h>
 
 #include "frameDefinitions.h"
+#include "youth_codec.h"
 #include "youth_cuda.h"
 
 #ifdef __cplusplus
@@ -30,6 +31,10 @@ extern "C" {
 /* color may be NULL: a constant-128 RGB plane is written so the record stays format-valid */
 int youth_bin_write_frame(FILE* f, uint32_t frame_id, uint32_t timestamp_ms, int width, int height,
                           const uint16_t* depth, const uint8_t* color);
+/* the same record with the depth payload packed by the YD16 codec (include/youth_codec.h):
+ * frameType = FRAME_TYPE_DEPTH_PACKED, depthDataSize = packed bytes; width/height say what it unpacks to */
+int youth_bin_write_packed_frame(FILE* f, uint32_t frame_id, uint32_t timestamp_ms, int width, int height,
+                                 const uint8_t* yd16, uint32_t yd16_bytes, const uint8_t* color);
 int youth_bin_write_eof(FILE* f);
 /* 1 = frame read, 0 = end of file / EOF marker / error / payload larger than the caps.
  * color may be NULL (payload skipped). */

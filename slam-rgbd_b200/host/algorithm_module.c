@@ -11,6 +11,7 @@
 #define _GNU_SOURCE
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <unistd.h>
 
 #include "algorithmModule.h"
@@ -18,6 +19,10 @@
 
 void youthSlamSetOptions(int lossless, int batch);
 void youthSlamDrain(void);
+int youthSlamProcessPackedFrames(const uint8_t* streams, const uint64_t* offsets, int n, int width, int height,
+                                 const uint32_t* timestamps);
+
+#define PACKED_RUN 64 /* packed records are gathered into runs of this many frames */
 
 void* algorithmModule(void* id) {
   const char* replay = (const char*)id;
@@ -38,10 +43,42 @@ void* algorithmModule(void* id) {
   uint16_t* depth = (uint16_t*)malloc(cap);
   FrameHeader hdr;
   long frames = 0;
-  while (depth && youth_bin_read_frame(f, &hdr, depth, cap, NULL, 0)) {
+  /* FRAME_TYPE_DEPTH_PACKED records (YD16, include/youth_codec.h) are gathered into runs and unpacked on the device */
+  uint8_t* run = NULL;
+  size_t run_cap = 0;
+  uint64_t offs[PACKED_RUN + 1] = {0};
+  uint32_t ts[PACKED_RUN];
+  int nrun = 0, rw = 0, rh = 0, failed = 0;
+  while (depth && !failed && youth_bin_read_frame(f, &hdr, depth, cap, NULL, 0)) {
+    if (hdr.frameType == FRAME_TYPE_DEPTH_PACKED) {
+      if (offs[nrun] + hdr.depthDataSize > run_cap) {
+        run_cap = 2 * (offs[nrun] + hdr.depthDataSize) + (1u << 20);
+        uint8_t* grown = (uint8_t*)realloc(run, run_cap);
+        if (!grown) break;
+        run = grown;
+      }
+      memcpy(run + offs[nrun], depth, hdr.depthDataSize);
+      offs[nrun + 1] = offs[nrun] + hdr.depthDataSize;
+      ts[nrun] = hdr.timestamp;
+      rw = hdr.width;
+      rh = hdr.height;
+      if (++nrun == PACKED_RUN) {
+        if (!youthSlamProcessPackedFrames(run, offs, nrun, rw, rh, ts)) failed = 1;
+        else frames += nrun;
+        nrun = 0;
+      }
+      continue;
+    }
+    if (nrun) { /* a raw record after packed ones: keep the order of the recording */
+      if (!youthSlamProcessPackedFrames(run, offs, nrun, rw, rh, ts)) break;
+      frames += nrun;
+      nrun = 0;
+    }
     if (!processSlamFrame((const int16_t*)depth, NULL, hdr.width, hdr.height, hdr.timestamp)) break;
     ++frames;
   }
+  if (nrun && !failed && youthSlamProcessPackedFrames(run, offs, nrun, rw, rh, ts)) frames += nrun;
+  free(run);
   fclose(f);
   free(depth);
   youthSlamDrain();

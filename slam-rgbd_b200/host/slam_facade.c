@@ -243,6 +243,46 @@ void youthSlamDrain(void) {
   pthread_mutex_unlock(&G.mu);
 }
 
+/* Replay of FRAME_TYPE_DEPTH_PACKED records: n YD16 streams back to back (offsets[n+1]) go to the device
+ * packed and are unpacked there (youth_cuda_track_batch_packed).  Lossless by construction; frames queued
+ * through processSlamFrame() before this call are tracked first, so the order of the recording is kept. */
+int youthSlamProcessPackedFrames(const uint8_t* streams, const uint64_t* offsets, int n, int width, int height,
+                                 const uint32_t* timestamps) {
+  if (!atomic_load(&G.running) || !G.h || !streams || !offsets || n < 1) return 0;
+  if (width != G.cfg.width || height != G.cfg.height) return 0;
+  float* poses = (float*)malloc(sizeof(float) * 12 * (size_t)G.batch);
+  if (!poses) return 0;
+  pthread_mutex_lock(&G.mu);
+  while (G.count > 0 || G.busy > 0) pthread_cond_wait(&G.idle, &G.mu); /* the worker is idle: the handle is ours */
+  int ok = 1;
+  for (int f0 = 0; f0 < n && ok; f0 += G.batch) {
+    const int cn = n - f0 < G.batch ? n - f0 : G.batch;
+    const uint8_t* sp[1] = {streams};
+    const uint64_t* op[1] = {offsets + f0};
+    ok = youth_cuda_track_batch_packed(G.h, sp, op, cn, YOUTH_MEM_HOST, timestamps ? timestamps + f0 : NULL, poses);
+    if (!ok) {
+      fprintf(stderr, "AlgorithmModule: packed tracking failed: %s\n", youth_cuda_last_error());
+      break;
+    }
+    atomic_store(&G.last_inliers, youth_cuda_last_inliers(G.h, 0));
+    G.accepted += cn;
+    G.tracked += cn;
+    if (G.pose_mq != (mqd_t)-1) {
+      const int base = youth_cuda_frame_count(G.h, 0) - cn;
+      const uint32_t inl = (uint32_t)atomic_load(&G.last_inliers);
+      char msg[sizeof(MessageHeader) + sizeof(YouthPoseMsg)];
+      for (int i = 0; i < cn; ++i) {
+        const size_t len = youth_pose_msg_build(msg, base + i, timestamps ? timestamps[f0 + i] : 0u,
+                                                poses + 12 * (size_t)i, 0u, inl);
+        if (mq_send(G.pose_mq, msg, len, 0) == 0) G.poses_sent++;
+      }
+    }
+  }
+  pthread_mutex_unlock(&G.mu);
+  free(poses);
+  return ok;
+}
+
 int youthSlamGetTrajectory(float* poses_out, uint32_t* timestamps_out, uint32_t* status_out, int max_frames) {
   if (!atomic_load(&G.running) || !G.h) return 0;
   int n = youth_cuda_get_trajectory(G.h, 0, 0, max_frames, poses_out, timestamps_out, status_out);

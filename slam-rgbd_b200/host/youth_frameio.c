@@ -18,17 +18,17 @@
 
 #include "youth_host.h"
 
-int youth_bin_write_frame(FILE* f, uint32_t frame_id, uint32_t timestamp_ms, int width, int height,
-                          const uint16_t* depth, const uint8_t* color) {
+static int write_record(FILE* f, uint32_t frame_id, uint32_t timestamp_ms, int width, int height, int frame_type,
+                        const void* depth, uint32_t depth_bytes, const uint8_t* color) {
   if (!f || !depth || width <= 0 || height <= 0 || width > 65535 || height > 65535) return 0;
   FrameHeader h;
   memset(&h, 0, sizeof(h)); /* also zeroes the 2 padding bytes the reference leaves undefined */
   h.frameId = frame_id;
   h.timestamp = timestamp_ms;
-  h.frameType = FRAME_TYPE_DEPTH_COLOR;
+  h.frameType = (uint16_t)frame_type;
   h.width = (uint16_t)width;
   h.height = (uint16_t)height;
-  h.depthDataSize = (uint32_t)((size_t)width * height * sizeof(uint16_t));
+  h.depthDataSize = depth_bytes;
   h.colorDataSize = (uint32_t)((size_t)width * height * 3);
   h.reserved = 0;
   if (fwrite(&h, sizeof(h), 1, f) != 1) return 0;
@@ -46,6 +46,19 @@ int youth_bin_write_frame(FILE* f, uint32_t frame_id, uint32_t timestamp_ms, int
     }
   }
   return 1;
+}
+
+int youth_bin_write_frame(FILE* f, uint32_t frame_id, uint32_t timestamp_ms, int width, int height,
+                          const uint16_t* depth, const uint8_t* color) {
+  if (width <= 0 || height <= 0) return 0;
+  return write_record(f, frame_id, timestamp_ms, width, height, FRAME_TYPE_DEPTH_COLOR, depth,
+                      (uint32_t)((size_t)width * height * sizeof(uint16_t)), color);
+}
+
+int youth_bin_write_packed_frame(FILE* f, uint32_t frame_id, uint32_t timestamp_ms, int width, int height,
+                                 const uint8_t* yd16, uint32_t yd16_bytes, const uint8_t* color) {
+  if (yd16_bytes < YOUTH_CODEC_HEADER_BYTES) return 0;
+  return write_record(f, frame_id, timestamp_ms, width, height, FRAME_TYPE_DEPTH_PACKED, yd16, yd16_bytes, color);
 }
 
 int youth_bin_write_eof(FILE* f) {

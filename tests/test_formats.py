@@ -129,6 +129,39 @@ def test_bin_edge_cases(host, tmp_path):
     assert len(got) == 2 and (got[0][5] == 128).all()
 
 
+def test_packed_depth_records(host, oracle, tmp_path):
+    """FRAME_TYPE_DEPTH_PACKED (2): the same record with a YD16 depth payload (include/youth_codec.h);
+    the reader is unchanged -- frameType and depthDataSize tell the consumer what it got."""
+    host.youth_bin_write_packed_frame.restype = C.c_int
+    host.youth_bin_write_packed_frame.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p,
+                                                  C.c_uint32, C.c_void_p]
+    depth, color = rand_frames(2, 64, 48)
+    depth[1] = (1200 + np.arange(64 * 48) // 7).astype(np.uint16).reshape(48, 64)
+    p = str(tmp_path / "p.bin")
+    f = libc.fopen(p.encode(), b"wb")
+    streams = [oracle.codec_encode(d) for d in depth]
+    for i, s in enumerate(streams):
+        assert host.youth_bin_write_packed_frame(f, i, 33 * i, 64, 48, s.ctypes.data, len(s), color[i].ctypes.data)
+    assert host.youth_bin_write_packed_frame(f, 9, 0, 64, 48, streams[0].ctypes.data, 8, None) == 0  # not even a header
+    assert host.youth_bin_write_frame(f, 2, 66, 64, 48, depth[0].ctypes.data, None)  # raw and packed records may mix
+    host.youth_bin_write_eof(f)
+    libc.fclose(f)
+    assert os.path.getsize(p) == sum(28 + len(s) + 64 * 48 * 3 for s in streams) + (28 + 64 * 48 * 5) + 28
+    f = libc.fopen(p.encode(), b"rb")
+    buf = np.empty(1 << 16, dtype=np.uint8)
+    c = np.empty((48, 64, 3), dtype=np.uint8)
+    hdr = FrameHeader()
+    for i, s in enumerate(streams):
+        assert host.youth_bin_read_frame(f, C.byref(hdr), buf.ctypes.data, buf.nbytes, c.ctypes.data, c.nbytes) == 1
+        assert (hdr.frameId, hdr.timestamp, hdr.frameType, hdr.width, hdr.height) == (i, 33 * i, 2, 64, 48)
+        assert hdr.depthDataSize == len(s) and np.array_equal(buf[:len(s)], s) and np.array_equal(c, color[i])
+        assert np.array_equal(oracle.codec_decode(buf[:hdr.depthDataSize], 64, 48), depth[i])
+    assert host.youth_bin_read_frame(f, C.byref(hdr), buf.ctypes.data, buf.nbytes, None, 0) == 1
+    assert hdr.frameType == 1 and hdr.depthDataSize == 64 * 48 * 2
+    assert host.youth_bin_read_frame(f, C.byref(hdr), buf.ctypes.data, buf.nbytes, None, 0) == 0
+    libc.fclose(f)
+
+
 def test_bin_large_frame_not_capped(host, tmp_path):
     """the reference playback path caps payloads at 1 MiB (loggingModule.c:528,424-427);
     1280x960 depth is 2.4 MB and must replay here."""

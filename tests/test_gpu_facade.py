@@ -99,6 +99,49 @@ def test_algorithm_module_replays_bin(pkg, small_seq, tmp_path):
     assert np.abs(rows[:, 1:4] - gt_rows[:, 1:4]).max() < 2e-3
 
 
+def test_packed_recording_replays_to_the_same_trajectory(pkg, oracle, tmp_path):
+    """raw .bin -> `youth_harness pack` (GPU YD16 encoder) -> replay through algorithmModule(): the packed
+    records are unpacked on the device and give the trajectory of the raw recording, text-identical."""
+    paths = pkg.lib_paths()
+    rec, pk = str(tmp_path / "rec.bin"), str(tmp_path / "rec_packed.bin")
+    assert subprocess.run([paths["harness"], "gen", rec, "70"], capture_output=True).returncode == 0
+    out = subprocess.run([paths["harness"], "pack", rec, pk], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert os.path.getsize(pk) < os.path.getsize(rec) - 70 * 350000  # depth shrank by more than half
+    # the packed file is a valid record stream: same headers except type/size, payload decodes to the raw depth
+    host = pkg.host_lib()
+    io = C.CDLL(paths["host"])  # private handle: argtypes set here do not leak into other tests
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    io.youth_bin_read_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    fa, fb = libc.fopen(rec.encode(), b"rb"), libc.fopen(pk.encode(), b"rb")
+    ha, hb = (C.c_uint8 * 28)(), (C.c_uint8 * 28)()
+    da, db = np.empty(640 * 480, dtype=np.uint16), np.empty(1 << 20, dtype=np.uint8)
+    for i in range(3):
+        assert io.youth_bin_read_frame(fa, ha, da.ctypes.data, da.nbytes, None, 0) == 1
+        assert io.youth_bin_read_frame(fb, hb, db.ctypes.data, db.nbytes, None, 0) == 1
+        a, b = np.frombuffer(bytes(ha), dtype=np.uint8), np.frombuffer(bytes(hb), dtype=np.uint8)
+        assert np.array_equal(a[:8], b[:8]) and np.array_equal(a[10:14], b[10:14]) and b[8] == 2  # FRAME_TYPE_DEPTH_PACKED
+        nbytes = int(np.frombuffer(bytes(hb), dtype=np.uint32)[4])
+        assert np.array_equal(oracle.codec_decode(db[:nbytes], 640, 480).ravel(), da)
+    libc.fclose(fa)
+    libc.fclose(fb)
+    rows = []
+    for path, tag in ((rec, "raw"), (pk, "packed")):
+        prefix = str(tmp_path / tag)
+        os.environ["YOUTH_SLAM_OUT"] = prefix
+        host.youthSlamSetOptions(1, 32)
+        th = threading.Thread(target=lambda: host.algorithmModule(C.c_char_p(path.encode())))
+        th.start()
+        th.join(timeout=120)
+        assert not th.is_alive()
+        del os.environ["YOUTH_SLAM_OUT"]
+        rows.append(open(prefix + "_trajectory.txt").read())
+    assert len(rows[0].splitlines()) == 70 and rows[0] == rows[1]
+
+
 def test_live_path_reference_chunks_to_tracker(pkg, small_seq):
     """(f)1 live path: frames leave through the REFERENCE's own sendMetadata/sendDataInChunks
     (oracle/_ref, compiled from loggingModule.c) over a real POSIX mq, are reassembled by
