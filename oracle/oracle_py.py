@@ -28,6 +28,13 @@ class OracleConfig(C.Structure):
     ]
 
 
+class TsdfConfig(C.Structure):
+    """Mirror of yo_tsdf_config (oracle/youth_tsdf_oracle.c) == youth_tsdf_config (include/youth_model.h)."""
+
+    _fields_ = [("dim", C.c_int32 * 3), ("voxel_m", C.c_float), ("origin", C.c_float * 3), ("trunc_m", C.c_float),
+                ("max_weight", C.c_int32), ("near_m", C.c_float), ("far_m", C.c_float)]
+
+
 class Level(C.Structure):
     _fields_ = [("w", C.c_int32), ("h", C.c_int32), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float),
                 ("cy", C.c_float)]
@@ -40,7 +47,7 @@ class Frame(C.Structure):
 
 def build(force=False):
     so = os.path.join(HERE, "_build", "libyouth_oracle_hwfma.so")
-    srcs = [os.path.join(HERE, f) for f in ("youth_oracle.c", "youth_codec_oracle.c", "youth_oracle.h")]
+    srcs = [os.path.join(HERE, f) for f in ("youth_oracle.c", "youth_codec_oracle.c", "youth_tsdf_oracle.c", "youth_oracle.h")]
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         subprocess.run(["make", "-C", HERE, "all"], check=True, capture_output=True)
     return so
@@ -96,6 +103,12 @@ def lib(fast=False):
             "yc_max_bytes": (C.c_size_t, [C.c_int, C.c_int]),
             "yc_encode": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
             "yc_decode": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]),
+            # frame-to-model statement (youth_tsdf_oracle.c)
+            "yo_tsdf_default_config": (None, [C.POINTER(TsdfConfig)]),
+            "yo_tsdf_clear": (None, [C.POINTER(TsdfConfig), C.c_void_p]),
+            "yo_tsdf_integrate": (None, [CP, C.POINTER(TsdfConfig), C.c_void_p, C.c_void_p, C.c_void_p]),
+            "yo_tsdf_raycast": (None, [CP, C.POINTER(TsdfConfig), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+            "yo_track_sequence_model": (None, [CP, C.POINTER(TsdfConfig), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
         })
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -152,7 +165,9 @@ class OFrame:
     def _view(self, field, level, ctype, comps):
         h, w = self.cfg.height >> level, self.cfg.width >> level
         p = getattr(self.ptr.contents, field)[level]
-        arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=(h * w * comps,))
+        buf = (ctype * (h * w * comps)).from_address(C.addressof(p.contents))
+        buf._owner = self  # the view keeps this frame (and so the C buffers) alive
+        arr = np.ctypeslib.as_array(buf)
         return arr.reshape((h, w, comps) if comps > 1 else (h, w))
 
     def depth(self, level):
@@ -218,3 +233,61 @@ def codec_decode(stream, w, h):
     out = np.empty((h, w), dtype=np.uint16)
     ok = lib().yc_decode(stream.ctypes.data, stream.size, w, h, out.ctypes.data)
     return out if ok else None
+
+
+# --------------------------------------------------------------------------- frame-to-model
+
+
+def tsdf_config(**overrides) -> TsdfConfig:
+    t = TsdfConfig()
+    lib().yo_tsdf_default_config(C.byref(t))
+    for k, v in overrides.items():
+        if k in ("dim", "origin"):
+            for i, x in enumerate(v):
+                getattr(t, k)[i] = x
+        else:
+            setattr(t, k, v)
+    return t
+
+
+def tsdf_config_from(product_tcfg) -> TsdfConfig:
+    t = TsdfConfig()
+    for name, _ in TsdfConfig._fields_:
+        if name in ("dim", "origin"):
+            for i in range(3):
+                getattr(t, name)[i] = getattr(product_tcfg, name)[i]
+        else:
+            setattr(t, name, getattr(product_tcfg, name))
+    return t
+
+
+def tsdf_new(tcfg):
+    """fresh volume: int16 [dz][dy][dx][2] = (32767, 0)"""
+    vol = np.empty((tcfg.dim[2], tcfg.dim[1], tcfg.dim[0], 2), dtype=np.int16)
+    lib().yo_tsdf_clear(C.byref(tcfg), vol.ctypes.data)
+    return vol
+
+
+def tsdf_integrate(cfg, tcfg, vol, depth0, pose):
+    depth0 = np.ascontiguousarray(depth0, dtype=np.float32)
+    pose = np.ascontiguousarray(pose, dtype=np.float32)
+    lib().yo_tsdf_integrate(C.byref(cfg), C.byref(tcfg), vol.ctypes.data, depth0.ctypes.data, pose.ctypes.data)
+
+
+def tsdf_raycast(cfg, tcfg, vol, pose, level):
+    h, w = cfg.height >> level, cfg.width >> level
+    pose = np.ascontiguousarray(pose, dtype=np.float32)
+    vmap = np.empty((h, w, 4), dtype=np.float32)
+    nmap = np.empty((h, w, 4), dtype=np.float32)
+    lib().yo_tsdf_raycast(C.byref(cfg), C.byref(tcfg), vol.ctypes.data, pose.ctypes.data, level, vmap.ctypes.data,
+                          nmap.ctypes.data)
+    return vmap, nmap
+
+
+def track_sequence_model(cfg, tcfg, frames):
+    assert frames.dtype == np.uint16 and frames.flags.c_contiguous
+    n = frames.shape[0]
+    poses = np.empty((n, 12), dtype=np.float32)
+    status = np.empty(n, dtype=np.uint32)
+    lib().yo_track_sequence_model(C.byref(cfg), C.byref(tcfg), frames.ctypes.data, n, poses.ctypes.data, status.ctypes.data)
+    return poses, status

@@ -9,6 +9,7 @@ from .binding import (  # noqa: F401
     CudaLibraryMissing,
     SynthConfig,
     Tracker,
+    TsdfConfig,
     YouthConfig,
     default_config,
     host_lib,
@@ -16,5 +17,6 @@ from .binding import (  # noqa: F401
     lib_paths,
     synth_gt,
     synth_sequence,
+    tsdf_config,
 )
 from .build import build_all  # noqa: F401

@@ -41,6 +41,13 @@ class YouthConfig(C.Structure):
     ]
 
 
+class TsdfConfig(C.Structure):
+    """Mirror of ``youth_tsdf_config`` (include/youth_model.h)."""
+
+    _fields_ = [("dim", C.c_int32 * 3), ("voxel_m", C.c_float), ("origin", C.c_float * 3), ("trunc_m", C.c_float),
+                ("max_weight", C.c_int32), ("near_m", C.c_float), ("far_m", C.c_float)]
+
+
 class SynthConfig(C.Structure):
     """Mirror of ``youth_synth_config`` (include/youth_host.h)."""
 
@@ -105,6 +112,14 @@ def cuda_lib():
         "youth_cuda_profile_read": (C.c_int, [H, C.c_void_p, C.c_void_p]),
         "youth_cuda_last_error": (C.c_char_p, []),
         "youth_cuda_abi_version": (C.c_int, []),
+        # include/youth_model.h
+        "youth_tsdf_default_config": (C.c_int, [C.POINTER(TsdfConfig)]),
+        "youth_cuda_enable_model": (C.c_int, [H, C.POINTER(TsdfConfig)]),
+        "youth_cuda_model_enabled": (C.c_int, [H]),
+        "youth_cuda_debug_read_volume": (C.c_int, [H, C.c_int, C.c_void_p, C.c_size_t]),
+        "youth_cuda_debug_read_model": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+        "youth_cuda_debug_integrate": (C.c_int, [H, C.c_int, C.c_int, C.c_void_p]),
+        "youth_cuda_debug_raycast": (C.c_int, [H, C.c_int, C.c_void_p]),
         # include/youth_codec.h
         "youth_codec_max_bytes": (C.c_size_t, [C.c_int, C.c_int]),
         "youth_codec_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(H)]),
@@ -189,6 +204,19 @@ def default_config(**overrides) -> YouthConfig:
         else:
             setattr(cfg, k, v)
     return cfg
+
+
+def tsdf_config(**overrides) -> TsdfConfig:
+    t = TsdfConfig()
+    if not cuda_lib().youth_tsdf_default_config(C.byref(t)):
+        raise RuntimeError("youth_tsdf_default_config failed")
+    for k, v in overrides.items():
+        if k in ("dim", "origin"):
+            for i, x in enumerate(v):
+                getattr(t, k)[i] = x
+        else:
+            setattr(t, k, v)
+    return t
 
 
 def synth_config(width=640, height=480, sequence=0, noise=0) -> SynthConfig:
@@ -318,6 +346,33 @@ class Tracker:
         self._check(self.lib.youth_cuda_debug_icp(self.h, stream, frame, level, pose.ctypes.data, sums.ctypes.data,
                                                   corr.ctypes.data if want_corr else None), "youth_cuda_debug_icp")
         return sums, corr
+
+    # ---- frame-to-model tracking (include/youth_model.h)
+    def enable_model(self, tcfg: TsdfConfig):
+        self.tcfg = tcfg
+        self._check(self.lib.youth_cuda_enable_model(self.h, C.byref(tcfg)), "youth_cuda_enable_model")
+
+    def read_volume(self, stream=0):
+        t = self.tcfg
+        vol = np.empty((t.dim[2], t.dim[1], t.dim[0], 2), dtype=np.int16)
+        self._check(self.lib.youth_cuda_debug_read_volume(self.h, stream, vol.ctypes.data, vol.nbytes),
+                    "youth_cuda_debug_read_volume")
+        return vol
+
+    def read_model(self, what, level, stream=0):
+        h, w = self.level_shape(level)
+        out = np.empty((h, w, 4), dtype=np.float32)
+        self._check(self.lib.youth_cuda_debug_read_model(self.h, what, stream, level, out.ctypes.data, out.nbytes),
+                    "youth_cuda_debug_read_model")
+        return out
+
+    def debug_integrate(self, frame, pose, stream=0):
+        pose = np.ascontiguousarray(pose, dtype=np.float32)
+        self._check(self.lib.youth_cuda_debug_integrate(self.h, stream, frame, pose.ctypes.data), "youth_cuda_debug_integrate")
+
+    def debug_raycast(self, pose, stream=0):
+        pose = np.ascontiguousarray(pose, dtype=np.float32)
+        self._check(self.lib.youth_cuda_debug_raycast(self.h, stream, pose.ctypes.data), "youth_cuda_debug_raycast")
 
     def timer_start(self):
         self._check(self.lib.youth_cuda_timer_start(self.h), "youth_cuda_timer_start")

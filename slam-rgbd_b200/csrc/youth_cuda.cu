@@ -22,6 +22,7 @@
 #include "youth_cuda.h"
 #include "youth_codec.h"
 #include "youth_kernels.cuh"
+#include "youth_model.cuh"
 
 #define YK_CHUNK_FRAMES 16 /* host-fed groups are copied + preprocessed in chunks of at least this many frames */
 #define YK_MAX_CHUNKS 64
@@ -109,6 +110,18 @@ struct youth_cuda_handle {
   int prof_n, prof_cap;
   double prof_ms[YOUTH_PROF_CLASSES];
   uint64_t prof_launches[YOUTH_PROF_CLASSES];
+  /* frame-to-model tracking (include/youth_model.h), off until youth_cuda_enable_model */
+  struct {
+    bool on;
+    youth_tsdf_config cfg;
+    TsdfGeom geom;
+    short2* vol;                     /* [S][dz][dy][dx] */
+    float2* maps[YOUTH_MAX_LEVELS];  /* [S][3][npix] ray-cast model maps */
+    float* world_f;                  /* [S][12] */
+    uint32_t* last_status;           /* [S] */
+    cudaGraphExec_t graph;           /* one frame of every sequence: stages 1-5, fusion, ray cast */
+    uint64_t graph_launches;
+  } m;
   /* packed (YD16) input path, created on first use (youth_cuda_track_batch_packed) */
   struct youth_codec* codec;
   unsigned long long* pk_h_off[2]; /* pinned: device offsets of the group's streams */
@@ -239,6 +252,11 @@ extern "C" void youth_cuda_destroy(youth_cuda_handle* h) {
   for (int g2 = 0; g2 < YK_GRAPH_SLOTS; ++g2)
     if (h->graphs[g2].exec) cudaGraphExecDestroy(h->graphs[g2].exec);
   cudaFree(h->corr_dbg);
+  cudaFree(h->m.vol);
+  for (int l = 0; l < YOUTH_MAX_LEVELS; ++l) cudaFree(h->m.maps[l]);
+  cudaFree(h->m.world_f);
+  cudaFree(h->m.last_status);
+  if (h->m.graph) cudaGraphExecDestroy(h->m.graph);
   if (h->codec) youth_codec_destroy(h->codec);
   for (int k = 0; k < 2; ++k) {
     if (h->pk_h_off[k]) cudaFreeHost(h->pk_h_off[k]);
@@ -423,6 +441,7 @@ static IcpParams icp_params(const youth_cuda_handle* h, int level, const RingGeo
   ip.pair_status = h->pair_status;
   ip.min_inliers = h->cfg.min_inliers;
   ip.do_solve = 1;
+  ip.model = h->m.on ? h->m.maps[level] : NULL;
   return ip;
 }
 
@@ -516,12 +535,176 @@ static int enqueue_icp(youth_cuda_handle* h, int n) {
     cp.last_inliers = h->last_inliers;
     cp.head = h->d_head;
     cp.cap = c.traj_capacity;
+    cp.world_f = h->m.on ? h->m.world_f : NULL;
+    cp.last_status = h->m.on ? h->m.last_status : NULL;
     ProfScope ps(h, YOUTH_PROF_MISC);
     k_compose<<<h->S, 128, 0, h->stream>>>(cp);
   }
   CU(cudaGetLastError());
   if (h->prof_on && h->prof_n > h->prof_cap - 256) return prof_flush(h);
   return 1;
+}
+
+/* ------------------------------------------------------------------ frame-to-model (include/youth_model.h) */
+
+extern "C" int youth_tsdf_default_config(youth_tsdf_config* t) {
+  if (!t) return fail("null config");
+  memset(t, 0, sizeof(*t));
+  t->dim[0] = 256;
+  t->dim[1] = 128;
+  t->dim[2] = 256;
+  t->voxel_m = 0.025f;
+  t->origin[0] = -3.2f;
+  t->origin[1] = -1.6f;
+  t->origin[2] = -1.2f;
+  t->trunc_m = 0.1f;
+  t->max_weight = 64;
+  t->near_m = 0.4f;
+  t->far_m = 8.0f;
+  return 1;
+}
+
+static size_t model_voxels(const youth_cuda_handle* h) {
+  return (size_t)h->m.geom.dx * h->m.geom.dy * h->m.geom.dz;
+}
+
+/* fresh volume (tsdf 1, weight 0) and empty model maps for sequence `stream` (-1 = all) */
+static int model_clear(youth_cuda_handle* h, int stream) {
+  const size_t nv = model_voxels(h);
+  const int s0 = stream < 0 ? 0 : stream, s1 = stream < 0 ? h->S : stream + 1;
+  k_fill_u32<<<1184, 256, 0, h->stream>>>(reinterpret_cast<uint32_t*>(h->m.vol + (size_t)s0 * nv), (size_t)(s1 - s0) * nv,
+                                          0x00007FFFu); /* short2 (32767, 0) */
+  h->launches++;
+  CU(cudaGetLastError());
+  return 1;
+}
+
+extern "C" int youth_cuda_model_enabled(const youth_cuda_handle* h) { return h && h->m.on ? 1 : 0; }
+
+extern "C" int youth_cuda_enable_model(youth_cuda_handle* h, const youth_tsdf_config* t) {
+  if (!h || !t) return fail("null argument");
+  if (h->m.on) return fail("frame-to-model tracking is already enabled");
+  if (h->total != 0) return fail("enable the model before the first frame (or after a full reset)");
+  for (int a = 0; a < 3; ++a)
+    if (t->dim[a] < 8 || t->dim[a] > 1024) return fail("tsdf dim[%d] must be 8..1024", a);
+  if (t->dim[0] % 8) return fail("tsdf dim[0] must be a multiple of 8");
+  if (!(t->voxel_m > 0.f) || !(t->trunc_m > 0.f)) return fail("voxel_m and trunc_m must be > 0");
+  if (t->max_weight < 1 || t->max_weight > 32767) return fail("max_weight must be 1..32767");
+  if (!(t->near_m > 0.f) || !(t->far_m > t->near_m)) return fail("need 0 < near_m < far_m");
+  CU(cudaSetDevice(h->cfg.device));
+  h->m.cfg = *t;
+  TsdfGeom& g = h->m.geom;
+  g.dx = t->dim[0];
+  g.dy = t->dim[1];
+  g.dz = t->dim[2];
+  g.vs = t->voxel_m;
+  g.inv_vs = 1.0f / t->voxel_m;
+  g.ox = t->origin[0];
+  g.oy = t->origin[1];
+  g.oz = t->origin[2];
+  g.mu = t->trunc_m;
+  g.step = t->trunc_m * 0.8f;
+  g.maxw = t->max_weight;
+  g.near_m = t->near_m;
+  g.far_m = t->far_m;
+  CU(dalloc(&h->m.vol, (size_t)h->S * model_voxels(h)));
+  for (int l = 0; l < h->cfg.levels; ++l) CU(dalloc(&h->m.maps[l], (size_t)h->S * 3 * h->npix[l]));
+  CU(dalloc(&h->m.world_f, (size_t)h->S * 12));
+  CU(dalloc(&h->m.last_status, (size_t)h->S));
+  h->m.on = true;
+  if (!model_clear(h, -1)) return 0;
+  CU(cudaStreamSynchronize(h->stream));
+  return 1;
+}
+
+/* fusion of the newest frame (slot < 0) or of ring slot `slot`, sequences [s0, s0 + ns) */
+static int enqueue_integrate(youth_cuda_handle* h, int s0, int ns, int slot, bool honour_status) {
+  IntegrateParams p;
+  memset(&p, 0, sizeof(p));
+  p.vol = h->m.vol;
+  p.t = h->m.geom;
+  p.depth0 = h->depth[0];
+  p.g = h->lv[0];
+  p.ring = ring_of(h, 1);
+  p.world_f = h->m.world_f;
+  p.last_status = honour_status ? h->m.last_status : NULL;
+  p.depth_factor = h->cfg.depth_factor;
+  p.slot = slot;
+  p.stream0 = s0;
+  const int zchunks = (p.t.dz + YM_ZCHUNK - 1) / YM_ZCHUNK;
+  const dim3 grid((p.t.dx + 31) / 32, (p.t.dy + 7) / 8, (unsigned)(ns * zchunks));
+  ProfScope ps(h, YOUTH_PROF_MODEL);
+  k_tsdf_integrate<<<grid, 256, 0, h->stream>>>(p);
+  CU(cudaGetLastError());
+  return 1;
+}
+
+static int enqueue_raycast(youth_cuda_handle* h, int s0, int ns) {
+  RaycastParams p;
+  memset(&p, 0, sizeof(p));
+  p.vol = h->m.vol;
+  p.t = h->m.geom;
+  int total = 0;
+  for (int l = 0; l < h->cfg.levels; ++l) {
+    p.model[l] = h->m.maps[l];
+    p.lv[l] = h->lv[l];
+    total += h->npix[l];
+  }
+  p.levels = h->cfg.levels;
+  p.world_f = h->m.world_f;
+  p.stream0 = s0;
+  const dim3 grid((total + 255) / 256, (unsigned)ns);
+  ProfScope ps(h, YOUTH_PROF_MODEL);
+  k_tsdf_raycast<<<grid, 256, 0, h->stream>>>(p);
+  CU(cudaGetLastError());
+  return 1;
+}
+
+/* one frame of every sequence: stages 1-5 against the model, fusion, ray cast */
+static int enqueue_model_frame(youth_cuda_handle* h, const uint16_t* const* raw_dev) {
+  return enqueue_preprocess(h, raw_dev, 1, 0, 1) && enqueue_icp(h, 1) && enqueue_integrate(h, 0, h->S, -1, true) &&
+         enqueue_raycast(h, 0, h->S);
+}
+
+static int finish_group(youth_cuda_handle* h, int n_frames, const uint32_t* timestamps_ms, float* poses_out);
+
+/* Frame-to-model groups are chains: frame after frame, each one H2D/D2D copy into a fixed landing
+ * slot followed by the captured graph of the whole per-frame schedule. */
+static int track_batch_model(youth_cuda_handle* h, const uint16_t* const* depth, int n_frames, int mem_kind,
+                             const uint32_t* timestamps_ms, float* poses_out) {
+  if (mem_kind != YOUTH_MEM_HOST && mem_kind != YOUTH_MEM_DEVICE && mem_kind != YOUTH_MEM_HOST_PINNED)
+    return fail("unknown mem_kind %d", mem_kind);
+  const size_t frame_px = (size_t)h->cfg.width * h->cfg.height, frame_bytes = frame_px * sizeof(uint16_t);
+  const uint16_t* dev_ptrs[YK_MAX_STREAMS];
+  for (int s = 0; s < h->S; ++s) dev_ptrs[s] = h->raw[0] + (size_t)s * frame_px;
+  const cudaMemcpyKind kind = mem_kind == YOUTH_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  for (int i = 0; i < n_frames; ++i) {
+    for (int s = 0; s < h->S; ++s) /* pageable sources are staged by the runtime before the call returns */
+      CU(cudaMemcpyAsync(h->raw[0] + (size_t)s * frame_px, depth[s] + (size_t)i * frame_px, frame_bytes, kind, h->stream));
+    if (h->graphs_enabled && !h->prof_on) {
+      if (!h->m.graph) {
+        cudaGraph_t graph = NULL;
+        const uint64_t before = h->launches;
+        CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        const int ok = enqueue_model_frame(h, dev_ptrs);
+        const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        if (!ok || ce != cudaSuccess || !graph) {
+          if (graph) cudaGraphDestroy(graph);
+          return fail("CUDA graph capture failed: %s", ce != cudaSuccess ? cudaGetErrorString(ce) : youth_cuda_last_error());
+        }
+        h->m.graph_launches = h->launches - before;
+        h->launches = before;
+        const cudaError_t ie = cudaGraphInstantiate(&h->m.graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+      }
+      CU(cudaGraphLaunch(h->m.graph, h->stream));
+      h->launches += h->m.graph_launches;
+    } else if (!enqueue_model_frame(h, dev_ptrs)) {
+      return 0;
+    }
+  }
+  return finish_group(h, n_frames, timestamps_ms, poses_out);
 }
 
 /* host bookkeeping of a group that has been enqueued, and the optional blocking pose read-back */
@@ -553,6 +736,7 @@ extern "C" int youth_cuda_track_batch(youth_cuda_handle* h, const uint16_t* cons
     if (h->h_count[s] + n_frames > h->cfg.traj_capacity) return fail("trajectory capacity (%d) exceeded", h->cfg.traj_capacity);
   }
   CU(cudaSetDevice(h->cfg.device));
+  if (h->m.on) return track_batch_model(h, depth, n_frames, mem_kind, timestamps_ms, poses_out);
   const size_t frame_px = (size_t)h->cfg.width * h->cfg.height;
   const size_t seq_bytes = frame_px * sizeof(uint16_t) * (size_t)n_frames;
   const uint16_t* dev_ptrs[YK_MAX_STREAMS];
@@ -646,6 +830,7 @@ extern "C" int youth_cuda_track_batch_packed(youth_cuda_handle* h, const uint8_t
   if (!h || !streams || !offsets) return fail("null argument");
   if (n_frames < 1 || n_frames > h->B) return fail("n_frames must be 1..batch (%d)", h->B);
   if (mem_kind != YOUTH_MEM_HOST && mem_kind != YOUTH_MEM_HOST_PINNED) return fail("packed input must be host memory");
+  if (h->m.on) return fail("packed input is not available in frame-to-model mode (unpack with youth_codec_decode)");
   for (int s = 0; s < h->S; ++s) {
     if (!streams[s] || !offsets[s]) return fail("streams[%d] / offsets[%d] is NULL", s, s);
     if (h->h_count[s] + n_frames > h->cfg.traj_capacity) return fail("trajectory capacity (%d) exceeded", h->cfg.traj_capacity);
@@ -753,6 +938,7 @@ extern "C" int youth_cuda_reset(youth_cuda_handle* h, int stream) {
     CU(cudaMemsetAsync(h->last_inliers + stream, 0, sizeof(int), h->stream));
     h->h_count[stream] = 0;
   }
+  if (h->m.on && !model_clear(h, stream)) return 0;
   return 1;
 }
 
@@ -819,6 +1005,85 @@ static int slot_of_frame(const youth_cuda_handle* h, int frame) {
   return (int)(frame % h->R);
 }
 
+/* the device keeps three float2 planes per map set; the read-back presents them as the float4
+ * (x, y, z, valid) maps / validity mask of the specification */
+static int read_planes(const float2* planes, size_t np, int what, void* dst, size_t dst_bytes) {
+  if (dst_bytes < (what == YOUTH_DBG_MASK ? np : np * 16)) return fail("dst too small");
+  float* tmp = (float*)malloc(np * 6 * sizeof(float));
+  if (!tmp) return fail("host allocation failed");
+  cudaError_t e = cudaMemcpy(tmp, planes, np * 6 * sizeof(float), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) {
+    free(tmp);
+    return fail("map read-back failed: %s", cudaGetErrorString(e));
+  }
+  for (size_t i = 0; i < np; ++i) {
+    const float vx = tmp[2 * i], vy = tmp[2 * i + 1], vz = tmp[2 * np + 2 * i];
+    const float nx = tmp[2 * np + 2 * i + 1], ny = tmp[4 * np + 2 * i], nz = tmp[4 * np + 2 * i + 1];
+    const int vok = vz > 0.0f, nok = YK_N_VALID(nx);
+    if (what == YOUTH_DBG_MASK) {
+      ((uint8_t*)dst)[i] = (uint8_t)(vok | (nok << 1));
+    } else {
+      float* o = (float*)dst + 4 * i;
+      if (what == YOUTH_DBG_VERTEX) {
+        o[0] = vx; o[1] = vy; o[2] = vz; o[3] = vok ? 1.0f : 0.0f;
+      } else {
+        o[0] = nok ? nx : 0.0f; o[1] = ny; o[2] = nz; o[3] = nok ? 1.0f : 0.0f;
+      }
+    }
+  }
+  free(tmp);
+  return 1;
+}
+
+extern "C" int youth_cuda_debug_read_volume(youth_cuda_handle* h, int stream, int16_t* dst, size_t dst_bytes) {
+  if (!h || !dst) return fail("null argument");
+  if (!h->m.on) return fail("frame-to-model tracking is not enabled");
+  if (stream < 0 || stream >= h->S) return fail("stream out of range");
+  const size_t nv = model_voxels(h);
+  if (dst_bytes < nv * 4) return fail("dst too small");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpy(dst, h->m.vol + (size_t)stream * nv, nv * 4, cudaMemcpyDeviceToHost));
+  return 1;
+}
+
+extern "C" int youth_cuda_debug_read_model(youth_cuda_handle* h, int what, int stream, int level, float* dst, size_t dst_bytes) {
+  if (!h || !dst) return fail("null argument");
+  if (!h->m.on) return fail("frame-to-model tracking is not enabled");
+  if (stream < 0 || stream >= h->S || level < 0 || level >= h->cfg.levels) return fail("stream/level out of range");
+  if (what != YOUTH_DBG_VERTEX && what != YOUTH_DBG_NORMAL) return fail("what must be YOUTH_DBG_VERTEX or YOUTH_DBG_NORMAL");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  const size_t np = (size_t)h->npix[level];
+  return read_planes(h->m.maps[level] + (size_t)stream * 3 * np, np, what, dst, dst_bytes);
+}
+
+static int slot_of_frame(const youth_cuda_handle* h, int frame);
+
+extern "C" int youth_cuda_debug_integrate(youth_cuda_handle* h, int stream, int frame, const float pose[12]) {
+  if (!h || !pose) return fail("null argument");
+  if (!h->m.on) return fail("frame-to-model tracking is not enabled");
+  if (stream < 0 || stream >= h->S) return fail("stream out of range");
+  const int slot = slot_of_frame(h, frame);
+  if (slot < 0) return fail("frame %d is not resident in the ring", frame);
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaMemcpyAsync(h->m.world_f + stream * 12, pose, sizeof(float) * 12, cudaMemcpyHostToDevice, h->stream));
+  if (!enqueue_integrate(h, stream, 1, slot, false)) return 0;
+  CU(cudaStreamSynchronize(h->stream));
+  return 1;
+}
+
+extern "C" int youth_cuda_debug_raycast(youth_cuda_handle* h, int stream, const float pose[12]) {
+  if (!h || !pose) return fail("null argument");
+  if (!h->m.on) return fail("frame-to-model tracking is not enabled");
+  if (stream < 0 || stream >= h->S) return fail("stream out of range");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaMemcpyAsync(h->m.world_f + stream * 12, pose, sizeof(float) * 12, cudaMemcpyHostToDevice, h->stream));
+  if (!enqueue_raycast(h, stream, 1)) return 0;
+  CU(cudaStreamSynchronize(h->stream));
+  return 1;
+}
+
 extern "C" int youth_cuda_debug_read(youth_cuda_handle* h, int what, int stream, int frame, int level, void* dst,
                                      size_t dst_bytes) {
   if (!h || !dst) return fail("null argument");
@@ -837,34 +1102,7 @@ extern "C" int youth_cuda_debug_read(youth_cuda_handle* h, int what, int stream,
     case YOUTH_DBG_VERTEX:
     case YOUTH_DBG_NORMAL:
     case YOUTH_DBG_MASK: {
-      /* the device keeps three float2 planes per slot; the read-back presents them as the
-       * float4 (x, y, z, valid) maps / validity mask of the specification */
-      if (dst_bytes < (what == YOUTH_DBG_MASK ? np : np * 16)) return fail("dst too small");
-      float* tmp = (float*)malloc(np * 6 * sizeof(float));
-      if (!tmp) return fail("host allocation failed");
-      cudaError_t e = cudaMemcpy(tmp, h->maps[level] + ((size_t)stream * h->R + slot) * 3 * np, np * 6 * sizeof(float),
-                                 cudaMemcpyDeviceToHost);
-      if (e != cudaSuccess) {
-        free(tmp);
-        return fail("map read-back failed: %s", cudaGetErrorString(e));
-      }
-      for (size_t i = 0; i < np; ++i) {
-        const float vx = tmp[2 * i], vy = tmp[2 * i + 1], vz = tmp[2 * np + 2 * i];
-        const float nx = tmp[2 * np + 2 * i + 1], ny = tmp[4 * np + 2 * i], nz = tmp[4 * np + 2 * i + 1];
-        const int vok = vz > 0.0f, nok = YK_N_VALID(nx);
-        if (what == YOUTH_DBG_MASK) {
-          ((uint8_t*)dst)[i] = (uint8_t)(vok | (nok << 1));
-        } else {
-          float* o = (float*)dst + 4 * i;
-          if (what == YOUTH_DBG_VERTEX) {
-            o[0] = vx; o[1] = vy; o[2] = vz; o[3] = vok ? 1.0f : 0.0f;
-          } else {
-            o[0] = nok ? nx : 0.0f; o[1] = ny; o[2] = nz; o[3] = nok ? 1.0f : 0.0f;
-          }
-        }
-      }
-      free(tmp);
-      return 1;
+      return read_planes(h->maps[level] + ((size_t)stream * h->R + slot) * 3 * np, np, what, dst, dst_bytes);
     }
     case YOUTH_DBG_PYRCNT:
       if (dst_bytes < np) return fail("dst too small");
