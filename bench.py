@@ -166,7 +166,9 @@ def host_threads():
 def base_config_dict(args, n_gpus):
     spg = getattr(args, "sequences_per_gpu", 1)
     w, h, lv = getattr(args, "width", W), getattr(args, "height", H), getattr(args, "levels", 3)
-    if (w, h, lv, spg) == (W, H, 3, 1):
+    if getattr(args, "mode", "frame") == "model":
+        name = "frame-to-model variant of configs[1]/[3] (TSDF 256x128x256 @ 25 mm, one captured graph per frame)"
+    elif (w, h, lv, spg) == (W, H, 3, 1):
         name = "configs[1]"
     elif (w, h, lv) == (W, H, 3):
         name = "configs[3]-style (several sequences per GPU)"
@@ -179,6 +181,7 @@ def base_config_dict(args, n_gpus):
                     f"ICP iterations fine->coarse = {iters}, 7x7 bilateral on, {spg} sequence(s) per GPU",
         "frames_per_step_per_gpu": FRAMES * spg,
         "batch_frames_per_launch_group": args.batch,
+        "icp_ppt": getattr(args, "ppt", 0) or 64,
         "sequences_per_gpu": spg,
         "partition": f"{n_gpus * spg} independent sequence(s), {spg} per GPU, no data-path collective",
         "l2": f"inputs ({raw_mb:.0f} MB raw depth per step) exceed the 126 MB L2 and are streamed once per step; "
@@ -247,6 +250,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     stream = torch.cuda.Stream()
+    if args.mode == "model" and not args.ppt:
+        args.ppt = 16  # a chain of single frames is latency-bound: more, shorter ICP runs per frame (part of the config)
     extra = {"icp_ppt": args.ppt} if args.ppt else {}
     Wd, Hd, S = args.width, args.height, args.sequences_per_gpu
     if (Wd, Hd) != (W, H):
@@ -254,6 +259,8 @@ def run_ours(args):
     cfg = pkg.default_config(batch=args.batch, n_streams=S, device=local, traj_capacity=FRAMES, levels=args.levels,
                              stream=stream.cuda_stream, **extra)
     trk = B.Tracker(cfg)
+    if args.mode == "model":  # frame-to-model tracking (include/youth_model.h): a sequence is a chain of frames
+        trk.enable_model(pkg.tsdf_config())
 
     # independent sequences: rank r tracks sequences r*S .. r*S+S-1 (seed 20261018 + sequence)
     t0 = time.perf_counter()
@@ -357,7 +364,7 @@ def run_ours(args):
     # ---- packed-input arm: the same step fed from YD16 streams (include/youth_codec.h) in pinned host
     # memory; the packed bytes cross PCIe and are unpacked on the device.  Reported next to e2e.
     packed_info = None
-    if not args.no_packed:
+    if not args.no_packed and args.mode != "model":
         cd = pkg.Codec(Wd, Hd, max_frames=FRAMES, device=local)
         enc = [cd.encode_ptr(d_base + k * seq_bytes, FRAMES, B.MEM_DEVICE) for k in range(S)]
         enc_ms = cd.last_kernel_ms()
@@ -432,7 +439,7 @@ def run_ours(args):
     achieved = bytes_per_launch / (icp0_ms * 1e-3) / 1e9 if icp0_ms > 0 else 0.0
     names = {B.PROF_INGEST: "k_ingest", B.PROF_NORMALS: "k_normals", B.PROF_ICP0: "k_icp_L0",
              B.PROF_ICP0 + 1: "k_icp_L1", B.PROF_ICP0 + 2: "k_icp_L2", B.PROF_ICP0 + 3: "k_icp_L3",
-             B.PROF_SOLVE: "k_solve", B.PROF_MISC: "k_compose"}
+             B.PROF_SOLVE: "k_tsdf_integrate", B.PROF_MISC: "k_compose", B.PROF_RAYCAST: "k_tsdf_raycast"}
     step_prof = {names[i]: {"ms": round(float(prof_ms[i]), 4), "launches": int(prof_n[i])}
                  for i in range(B.PROF_CLASSES) if prof_n[i]}
 
@@ -451,14 +458,14 @@ def run_ours(args):
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
-        if (Wd, Hd, S, args.levels) == (W, H, 1, 3) and tj.get("pairs_per_launch") == args.batch:
+        if (Wd, Hd, S, args.levels) == (W, H, 1, 3) and tj.get("pairs_per_launch") == args.batch and args.mode == "frame":
             traffic = tj.get("k_icp_L0_dram_bytes_per_launch")
     except Exception:
         pass
 
     # ---- live mode: one frame per call (youth_cuda_track), pose read back every frame
     streaming = None
-    if (Wd, Hd, S) == (W, H, 1):
+    if (Wd, Hd, S) == (W, H, 1) and args.mode != "model":
         live = B.Tracker(pkg.default_config(batch=1, device=local, traj_capacity=128, levels=args.levels,
                                             **({"icp_ppt": args.ppt} if args.ppt else {})))
         for i in range(8):
@@ -527,6 +534,8 @@ def main():
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--levels", type=int, default=3)
     ap.add_argument("--no-packed", action="store_true", help="skip the YD16 packed-input arm")
+    ap.add_argument("--mode", default="frame", choices=["frame", "model"],
+                    help="frame = frame-to-frame (the headline workload), model = frame-to-model (TSDF fusion + ray cast)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -159,9 +159,11 @@ int youth_cuda_timer_stop(youth_cuda_handle* h, float* ms_out);
 #define YOUTH_PROF_INGEST 0  /* k_ingest: depth ingest + bilateral + pyramid + vertex maps */
 #define YOUTH_PROF_NORMALS 1 /* k_normals */
 #define YOUTH_PROF_ICP0 2    /* k_icp at level 0 (ICP0 + l = level l) */
-#define YOUTH_PROF_SOLVE 6   /* unused since the solve moved into k_icp's last tile */
-#define YOUTH_PROF_MISC 7    /* k_compose */
-#define YOUTH_PROF_CLASSES 8
+#define YOUTH_PROF_SOLVE 6   /* (was k_solve: the solve moved into k_icp's last run) now k_tsdf_integrate */
+#define YOUTH_PROF_INTEGRATE YOUTH_PROF_SOLVE
+#define YOUTH_PROF_MISC 7    /* k_compose, YD16 unpacking */
+#define YOUTH_PROF_RAYCAST 8 /* k_tsdf_raycast */
+#define YOUTH_PROF_CLASSES 9
 int youth_cuda_profile_enable(youth_cuda_handle* h, int on);
 int youth_cuda_profile_read(youth_cuda_handle* h, double* ms_out, uint64_t* launches_out);
 

@@ -16,7 +16,9 @@
  *   k_icp x (iterations)             stages 3-5 against the model maps
  *   k_compose                        pose chain
  *   k_tsdf_integrate                 fuse the frame at its new pose (skipped when flagged LOST)
- *   k_tsdf_raycast                   model maps of every pyramid level from the new pose
+ *   k_tsdf_raycast, k_normals        model vertex maps of every pyramid level from the new pose (each ray
+ *                                    starts just in front of the depth the fused frame measured at its
+ *                                    pixel) and their cross-product normals (stage 2b, unchanged)
  * A sequence is a chain here (frame t needs the pose of t-1), so throughput comes from tracking
  * several independent sequences per launch (cfg.n_streams), each with its own volume.
  *
@@ -61,11 +63,11 @@ int youth_cuda_debug_read_volume(youth_cuda_handle* h, int stream, int16_t* dst,
 /* model maps of `level`: what = YOUTH_DBG_VERTEX / YOUTH_DBG_NORMAL, float [h][w][4] = x, y, z, valid */
 int youth_cuda_debug_read_model(youth_cuda_handle* h, int what, int stream, int level, float* dst, size_t dst_bytes);
 /* run ONE kernel outside the tracking schedule: fuse resident frame `frame` of `stream` at `pose`
- * (camera-to-world 3x4) / ray-cast every level from `pose` into the model maps */
+ * (camera-to-world 3x4) / ray-cast every level from `pose` into the model maps.
+ * hint_frame >= 0: search every ray only from 1.25 mu in front of to 2 mu behind the depth that resident
+ * frame measured at the pixel (what the tracker does with the frame it has just fused); -1: whole range */
 int youth_cuda_debug_integrate(youth_cuda_handle* h, int stream, int frame, const float pose[12]);
-int youth_cuda_debug_raycast(youth_cuda_handle* h, int stream, const float pose[12]);
-
-#define YOUTH_PROF_MODEL YOUTH_PROF_SOLVE /* profile class of k_tsdf_integrate + k_tsdf_raycast (the old k_solve slot) */
+int youth_cuda_debug_raycast(youth_cuda_handle* h, int stream, const float pose[12], int hint_frame);
 
 #ifdef __cplusplus
 }

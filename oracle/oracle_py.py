@@ -107,7 +107,8 @@ def lib(fast=False):
             "yo_tsdf_default_config": (None, [C.POINTER(TsdfConfig)]),
             "yo_tsdf_clear": (None, [C.POINTER(TsdfConfig), C.c_void_p]),
             "yo_tsdf_integrate": (None, [CP, C.POINTER(TsdfConfig), C.c_void_p, C.c_void_p, C.c_void_p]),
-            "yo_tsdf_raycast": (None, [CP, C.POINTER(TsdfConfig), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+            "yo_tsdf_raycast": (None, [CP, C.POINTER(TsdfConfig), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
             "yo_track_sequence_model": (None, [CP, C.POINTER(TsdfConfig), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
         })
     for name, (res, args) in sig.items():
@@ -274,13 +275,17 @@ def tsdf_integrate(cfg, tcfg, vol, depth0, pose):
     lib().yo_tsdf_integrate(C.byref(cfg), C.byref(tcfg), vol.ctypes.data, depth0.ctypes.data, pose.ctypes.data)
 
 
-def tsdf_raycast(cfg, tcfg, vol, pose, level):
+def tsdf_raycast(cfg, tcfg, vol, pose, level, hint=None):
+    """hint: optional float32 depth map of this level (raw units) seen from `pose` (march start, see the C file)"""
     h, w = cfg.height >> level, cfg.width >> level
     pose = np.ascontiguousarray(pose, dtype=np.float32)
     vmap = np.empty((h, w, 4), dtype=np.float32)
     nmap = np.empty((h, w, 4), dtype=np.float32)
-    lib().yo_tsdf_raycast(C.byref(cfg), C.byref(tcfg), vol.ctypes.data, pose.ctypes.data, level, vmap.ctypes.data,
-                          nmap.ctypes.data)
+    if hint is not None:
+        hint = np.ascontiguousarray(hint, dtype=np.float32)
+        assert hint.shape == (h, w)
+    lib().yo_tsdf_raycast(C.byref(cfg), C.byref(tcfg), vol.ctypes.data, pose.ctypes.data, level,
+                          hint.ctypes.data if hint is not None else None, vmap.ctypes.data, nmap.ctypes.data)
     return vmap, nmap
 
 

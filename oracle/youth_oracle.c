@@ -209,6 +209,11 @@ void yo_vertex_normal(const yo_config* c, int level, const float* depth, float* 
       }
     }
   }
+  yo_normals_from_vertices(W, H, vmap, nmap);
+}
+
+/* normal = normalize((V(u+1,v) - V) x (V(u,v+1) - V)); valid iff the three vertices are */
+void yo_normals_from_vertices(int W, int H, const float* vmap, float* nmap) {
   for (int v = 0; v < H; ++v) {
     for (int u = 0; u < W; ++u) {
       float* o = nmap + 4 * (size_t)(v * W + u);

@@ -85,6 +85,8 @@ void yo_bilateral(const yo_config* cfg, const uint16_t* raw, float* depth0);
 void yo_pyrdown(const yo_config* cfg, int w, int h, const float* src, float* dst, uint8_t* cnt);
 /* stage 2: vertex + normal maps of one level */
 void yo_vertex_normal(const yo_config* cfg, int level, const float* depth, float* vmap, float* nmap);
+/* the normal half of stage 2 on its own (also used on ray-cast model vertex maps) */
+void yo_normals_from_vertices(int w, int h, const float* vmap, float* nmap);
 /* stages 1+2 for all levels */
 void yo_preprocess(const yo_config* cfg, const uint16_t* raw, yo_frame* out);
 

@@ -144,9 +144,14 @@ static int tsdf_trilinear(const yo_tsdf_config* t, const int16_t* vox, float gx,
 /* Ray-cast the model from `pose` (camera-to-world) at pyramid level `level` into float4 vertex and
  * normal maps (x, y, z, valid) expressed in THAT camera's frame, i.e. the maps a frame taken from
  * `pose` would have -- which is what stage 3 expects of a "previous frame".  The ray parameter is
- * the depth z: point(l) = l * ((u - cx)/fx, (v - cy)/fy, 1) in the camera frame. */
+ * the depth z: point(l) = l * ((u - cx)/fx, (v - cy)/fy, 1) in the camera frame.
+ * hint (nullable): a depth map of this level (raw units, 0 = invalid) taken from `pose` -- the tracker
+ * passes the frame it has just fused.  Where it has a reading (the pixel's own, else the nearest one in
+ * its group of 32 consecutive pixels) the march starts 1.25 mu in front of it and gives up 2 mu behind it,
+ * instead of walking from the near plane to the far end of the volume (the surface seen from this pose is there), which removes the walk through
+ * empty space; everything else is unchanged. */
 void yo_tsdf_raycast(const yo_config* c, const yo_tsdf_config* t, const int16_t* vox, const float pose[12], int level,
-                     float* vmap, float* nmap) {
+                     const float* hint, float* vmap, float* nmap) {
   yo_level g;
   yo_level_geometry(c, level, &g);
   const float inv_vs = 1.0f / t->voxel_m;
@@ -183,6 +188,23 @@ void yo_tsdf_raycast(const yo_config* c, const yo_tsdf_config* t, const int16_t*
       }
       if (miss || !(lmin < lmax)) continue;
       float lam = lmin;
+      if (hint != NULL) {
+        /* own reading, else the nearest reading among the 32 consecutive pixels (row-major index) this pixel
+         * belongs to -- the group one warp ray-casts on the device, so no lane walks alone from the near plane */
+        float D = hint[(size_t)v * g.w + u];
+        if (!(D > 0.0f)) {
+          const size_t p = (size_t)v * g.w + u, g0 = p & ~(size_t)31, np = (size_t)g.w * g.h;
+          D = 0.0f;
+          for (size_t q = g0; q < g0 + 32 && q < np; ++q)
+            if (hint[q] > 0.0f && (D == 0.0f || hint[q] < D)) D = hint[q];
+        }
+        if (D > 0.0f) {
+          const float zh = D / c->depth_factor;
+          const float start = zh - t->trunc_m * 1.25f, stop = zh + t->trunc_m * 2.0f;
+          if (start > lam) lam = start;
+          if (stop < lmax) lmax = stop; /* the surface fused from this reading is inside this window or nowhere */
+        }
+      }
       float fprev = tsdf_nearest(t, vox, fmaf(lam, dg[0], og[0]), fmaf(lam, dg[1], og[1]), fmaf(lam, dg[2], og[2]));
       for (;;) {
         /* inside the truncation band in front of a surface the step shrinks with the distance (never below
@@ -207,26 +229,6 @@ void yo_tsdf_raycast(const yo_config* c, const yo_tsdf_config* t, const int16_t*
             vo[0] = ((float)u - g.cx) * ls / g.fx;
             vo[1] = ((float)v - g.cy) * ls / g.fy;
             vo[3] = 1.0f;
-            const float gx = fmaf(ls, dg[0], og[0]), gy = fmaf(ls, dg[1], og[1]), gz = fmaf(ls, dg[2], og[2]);
-            float xp, xm, yp, ym, zp, zm;
-            if (tsdf_trilinear(t, vox, gx + 1.0f, gy, gz, &xp) && tsdf_trilinear(t, vox, gx - 1.0f, gy, gz, &xm) &&
-                tsdf_trilinear(t, vox, gx, gy + 1.0f, gz, &yp) && tsdf_trilinear(t, vox, gx, gy - 1.0f, gz, &ym) &&
-                tsdf_trilinear(t, vox, gx, gy, gz + 1.0f, &zp) && tsdf_trilinear(t, vox, gx, gy, gz - 1.0f, &zm)) {
-              const float nwx = xp - xm, nwy = yp - ym, nwz = zp - zm;
-              /* world -> camera (R^T); the tsdf grows towards the camera, the maps of stage 2 carry normals
-               * that point away from it (cross(dx, dy) of a fronto-parallel plane is +z), hence the minus */
-              const float ncx = fmaf(pose[0], nwx, fmaf(pose[4], nwy, pose[8] * nwz));
-              const float ncy = fmaf(pose[1], nwx, fmaf(pose[5], nwy, pose[9] * nwz));
-              const float ncz = fmaf(pose[2], nwx, fmaf(pose[6], nwy, pose[10] * nwz));
-              const float len2 = (ncx * ncx + ncy * ncy) + ncz * ncz;
-              if (len2 > 1e-24f) {
-                const float inv = 1.0f / sqrtf(len2);
-                no[0] = -(ncx * inv);
-                no[1] = -(ncy * inv);
-                no[2] = -(ncz * inv);
-                no[3] = 1.0f;
-              }
-            }
             break;
           }
         }
@@ -235,6 +237,9 @@ void yo_tsdf_raycast(const yo_config* c, const yo_tsdf_config* t, const int16_t*
       }
     }
   }
+  /* model normals: the normal half of stage 2 applied to the ray-cast vertex map (same convention as the
+   * frame maps by construction, and a third of the volume reads of a tsdf-gradient normal) */
+  yo_normals_from_vertices(g.w, g.h, vmap, nmap);
 }
 
 /* ------------------------------------------------------------------ frame-to-model sequence tracker */
@@ -291,7 +296,7 @@ uint32_t yo_model_tracker_track(yo_model_tracker* m, const uint16_t* raw, float 
   for (int i = 0; i < 12; ++i) pf[i] = (float)m->world[i];
   if (!(status & YO_STATUS_LOST)) yo_tsdf_integrate(&m->cfg, &m->tcfg, m->vox, m->cur->depth[0], pf);
   for (int l = 0; l < m->cfg.levels; ++l)
-    yo_tsdf_raycast(&m->cfg, &m->tcfg, m->vox, pf, l, m->model->vmap[l], m->model->nmap[l]);
+    yo_tsdf_raycast(&m->cfg, &m->tcfg, m->vox, pf, l, m->cur->depth[l], m->model->vmap[l], m->model->nmap[l]);
   m->count++;
   if (pose_out) memcpy(pose_out, pf, sizeof(pf));
   return status;

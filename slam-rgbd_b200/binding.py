@@ -11,7 +11,8 @@ SUM_SLOTS = 32
 MEM_HOST, MEM_DEVICE, MEM_HOST_PINNED = 0, 1, 2
 DBG_DEPTH, DBG_VERTEX, DBG_NORMAL, DBG_MASK, DBG_PYRCNT = 1, 2, 3, 4, 5
 STATUS_FIRST, STATUS_LOST = 1, 2
-PROF_INGEST, PROF_NORMALS, PROF_ICP0, PROF_SOLVE, PROF_MISC, PROF_CLASSES = 0, 1, 2, 6, 7, 8
+PROF_INGEST, PROF_NORMALS, PROF_ICP0, PROF_SOLVE, PROF_MISC, PROF_RAYCAST, PROF_CLASSES = 0, 1, 2, 6, 7, 8, 9
+PROF_INTEGRATE = PROF_SOLVE
 
 
 class CudaLibraryMissing(RuntimeError):
@@ -119,7 +120,7 @@ def cuda_lib():
         "youth_cuda_debug_read_volume": (C.c_int, [H, C.c_int, C.c_void_p, C.c_size_t]),
         "youth_cuda_debug_read_model": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
         "youth_cuda_debug_integrate": (C.c_int, [H, C.c_int, C.c_int, C.c_void_p]),
-        "youth_cuda_debug_raycast": (C.c_int, [H, C.c_int, C.c_void_p]),
+        "youth_cuda_debug_raycast": (C.c_int, [H, C.c_int, C.c_void_p, C.c_int]),
         # include/youth_codec.h
         "youth_codec_max_bytes": (C.c_size_t, [C.c_int, C.c_int]),
         "youth_codec_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(H)]),
@@ -370,9 +371,10 @@ class Tracker:
         pose = np.ascontiguousarray(pose, dtype=np.float32)
         self._check(self.lib.youth_cuda_debug_integrate(self.h, stream, frame, pose.ctypes.data), "youth_cuda_debug_integrate")
 
-    def debug_raycast(self, pose, stream=0):
+    def debug_raycast(self, pose, stream=0, hint_frame=-1):
         pose = np.ascontiguousarray(pose, dtype=np.float32)
-        self._check(self.lib.youth_cuda_debug_raycast(self.h, stream, pose.ctypes.data), "youth_cuda_debug_raycast")
+        self._check(self.lib.youth_cuda_debug_raycast(self.h, stream, pose.ctypes.data, hint_frame),
+                    "youth_cuda_debug_raycast")
 
     def timer_start(self):
         self._check(self.lib.youth_cuda_timer_start(self.h), "youth_cuda_timer_start")

@@ -633,13 +633,14 @@ static int enqueue_integrate(youth_cuda_handle* h, int s0, int ns, int slot, boo
   p.stream0 = s0;
   const int zchunks = (p.t.dz + YM_ZCHUNK - 1) / YM_ZCHUNK;
   const dim3 grid((p.t.dx + 31) / 32, (p.t.dy + 7) / 8, (unsigned)(ns * zchunks));
-  ProfScope ps(h, YOUTH_PROF_MODEL);
+  ProfScope ps(h, YOUTH_PROF_INTEGRATE);
   k_tsdf_integrate<<<grid, 256, 0, h->stream>>>(p);
   CU(cudaGetLastError());
   return 1;
 }
 
-static int enqueue_raycast(youth_cuda_handle* h, int s0, int ns) {
+/* hint_slot: -2 = no march-start hint, -1 = the newest frame's depth pyramid, >= 0 = that ring slot */
+static int enqueue_raycast(youth_cuda_handle* h, int s0, int ns, int hint_slot) {
   RaycastParams p;
   memset(&p, 0, sizeof(p));
   p.vol = h->m.vol;
@@ -648,14 +649,42 @@ static int enqueue_raycast(youth_cuda_handle* h, int s0, int ns) {
   for (int l = 0; l < h->cfg.levels; ++l) {
     p.model[l] = h->m.maps[l];
     p.lv[l] = h->lv[l];
-    total += h->npix[l];
+    total += (h->npix[l] + 31) & ~31; /* every level padded to whole warps */
   }
   p.levels = h->cfg.levels;
   p.world_f = h->m.world_f;
   p.stream0 = s0;
+  for (int l = 0; l < h->cfg.levels; ++l) p.depth[l] = h->depth[l];
+  p.ring = ring_of(h, 1);
+  p.hint = hint_slot >= -1;
+  p.hint_slot = hint_slot;
+  p.depth_factor = h->cfg.depth_factor;
   const dim3 grid((total + 255) / 256, (unsigned)ns);
-  ProfScope ps(h, YOUTH_PROF_MODEL);
-  k_tsdf_raycast<<<grid, 256, 0, h->stream>>>(p);
+  {
+    ProfScope ps(h, YOUTH_PROF_RAYCAST);
+    k_tsdf_raycast<<<grid, 256, 0, h->stream>>>(p);
+  }
+  /* model normals = stage 2b on the ray-cast vertex maps (every level): the model maps are a one-slot ring */
+  {
+    NormalParams np;
+    memset(&np, 0, sizeof(np));
+    int px = 0;
+    for (int l = 0; l < h->cfg.levels; ++l) {
+      np.maps[l] = h->m.maps[l] + (size_t)s0 * 3 * h->npix[l];
+      np.lv[l] = h->lv[l];
+      px += h->npix[l];
+    }
+    np.first_level = 0;
+    np.ring = ring_of(h, 1);
+    np.ring.R = 1;
+    np.ring.S = ns;
+    np.frame0 = 0;
+    np.chunk_n = 1;
+    np.levels = h->cfg.levels;
+    const dim3 ngrid((px + 255) / 256, (unsigned)ns);
+    ProfScope ps(h, YOUTH_PROF_RAYCAST);
+    k_normals<<<ngrid, 256, 0, h->stream>>>(np);
+  }
   CU(cudaGetLastError());
   return 1;
 }
@@ -663,7 +692,7 @@ static int enqueue_raycast(youth_cuda_handle* h, int s0, int ns) {
 /* one frame of every sequence: stages 1-5 against the model, fusion, ray cast */
 static int enqueue_model_frame(youth_cuda_handle* h, const uint16_t* const* raw_dev) {
   return enqueue_preprocess(h, raw_dev, 1, 0, 1) && enqueue_icp(h, 1) && enqueue_integrate(h, 0, h->S, -1, true) &&
-         enqueue_raycast(h, 0, h->S);
+         enqueue_raycast(h, 0, h->S, -1);
 }
 
 static int finish_group(youth_cuda_handle* h, int n_frames, const uint32_t* timestamps_ms, float* poses_out);
@@ -1073,13 +1102,18 @@ extern "C" int youth_cuda_debug_integrate(youth_cuda_handle* h, int stream, int 
   return 1;
 }
 
-extern "C" int youth_cuda_debug_raycast(youth_cuda_handle* h, int stream, const float pose[12]) {
+extern "C" int youth_cuda_debug_raycast(youth_cuda_handle* h, int stream, const float pose[12], int hint_frame) {
   if (!h || !pose) return fail("null argument");
   if (!h->m.on) return fail("frame-to-model tracking is not enabled");
   if (stream < 0 || stream >= h->S) return fail("stream out of range");
+  int hint_slot = -2;
+  if (hint_frame >= 0) {
+    hint_slot = slot_of_frame(h, hint_frame);
+    if (hint_slot < 0) return fail("frame %d is not resident in the ring", hint_frame);
+  }
   CU(cudaSetDevice(h->cfg.device));
   CU(cudaMemcpyAsync(h->m.world_f + stream * 12, pose, sizeof(float) * 12, cudaMemcpyHostToDevice, h->stream));
-  if (!enqueue_raycast(h, stream, 1)) return 0;
+  if (!enqueue_raycast(h, stream, 1, hint_slot)) return 0;
   CU(cudaStreamSynchronize(h->stream));
   return 1;
 }

@@ -8,9 +8,11 @@
  *                     voxels.  A voxel is READ ONLY IF it is updated, so the traffic is the
  *                     visible truncation band, not the volume.
  *   k_tsdf_raycast    one thread per pixel of every pyramid level: march the ray in steps of
- *                     0.8 mu (shrinking inside the truncation band) on nearest-voxel samples, refine the zero crossing with two
- *                     trilinear samples, gradient normal from six more; writes the model maps
- *                     in the three-float2-plane layout k_icp gathers from.
+ *                     0.8 mu (shrinking inside the truncation band) on nearest-voxel samples, starting
+ *                     just in front of the depth the fused frame measured there; refine the zero crossing with two
+ *                     trilinear samples; writes the model vertex map in the three-float2-plane layout
+ *                     k_icp gathers from.  The model normals are the cross-product normals of that
+ *                     vertex map: k_normals (stage 2b) runs over the model maps right after.
  *   k_fill_u32        volume reset
  *
  * Same arithmetic contract as youth_kernels.cuh (--fmad=false, explicit fma where specified,
@@ -59,6 +61,12 @@ struct RaycastParams {
   int levels;
   const float* world_f;
   int stream0;
+  /* march-start hint: the depth pyramid of a resident frame taken from the same pose (the frame just fused) */
+  const float* depth[YOUTH_MAX_LEVELS]; /* [S][R][npix_l]; used when hint != 0 */
+  RingGeom ring;
+  int hint;      /* 0: start at the near plane */
+  int hint_slot; /* >= 0: this ring slot; < 0: the newest frame (head - 1) */
+  float depth_factor;
 };
 
 __global__ void __launch_bounds__(256) k_fill_u32(uint32_t* p, size_t n, uint32_t v) {
@@ -164,15 +172,19 @@ __device__ __forceinline__ bool tsdf_trilinear(const short2* __restrict__ vol, c
 __global__ void __launch_bounds__(256) k_tsdf_raycast(const __grid_constant__ RaycastParams P) {
   int p = blockIdx.x * 256 + threadIdx.x;
   const int s = P.stream0 + blockIdx.y;
+  /* levels are laid out one after the other, each padded to a multiple of 32 pixels, so a warp never
+   * straddles two levels and its 32 lanes are the specification's group of 32 consecutive pixels */
   int level = 0;
   for (; level < P.levels; ++level) {
-    const int np = P.lv[level].w * P.lv[level].h;
-    if (p < np) break;
-    p -= np;
+    const int np_pad = (P.lv[level].w * P.lv[level].h + 31) & ~31;
+    if (p < np_pad) break;
+    p -= np_pad;
   }
-  if (level >= P.levels) return;
+  if (level >= P.levels) return; /* warp-uniform */
   const LevelGeom g = P.lv[level];
   const size_t npix = (size_t)g.w * g.h;
+  const bool in_level = (size_t)p < npix; /* padding lanes still take part in the warp reduction below */
+  if (!in_level) p = (int)npix - 1;
   const int v = p / g.w, u = p - v * g.w;
   const TsdfGeom& t = P.t;
   const short2* __restrict__ vol = P.vol + (size_t)s * t.dx * t.dy * t.dz;
@@ -181,7 +193,7 @@ __global__ void __launch_bounds__(256) k_tsdf_raycast(const __grid_constant__ Ra
 #pragma unroll
   for (int k = 0; k < 12; ++k) R[k] = __ldg(T + k);
 
-  float vx = 0.0f, vy = 0.0f, vz = 0.0f, nx = YK_N_INVALID, ny = 0.0f, nz = 0.0f;
+  float vx = 0.0f, vy = 0.0f, vz = 0.0f;
   const float ogx = (R[3] - t.ox) * t.inv_vs - 0.5f, ogy = (R[7] - t.oy) * t.inv_vs - 0.5f, ogz = (R[11] - t.oz) * t.inv_vs - 0.5f;
   const float dcx = ((float)u - g.cx) / g.fx, dcy = ((float)v - g.cy) / g.fy;
   const float dgx = __fmaf_rn(R[0], dcx, __fmaf_rn(R[1], dcy, R[2])) * t.inv_vs;
@@ -208,8 +220,27 @@ __global__ void __launch_bounds__(256) k_tsdf_raycast(const __grid_constant__ Ra
       }
     }
   }
+  /* march-start hint: own reading, else the nearest reading of the warp's 32 consecutive pixels (level
+   * sizes are multiples of 32 pixels or the group is cut at the end of the level, as in the specification);
+   * evaluated by every lane before any lane leaves, so the warp reduction is complete */
+  float hintD = 0.0f;
+  if (P.hint) {
+    const int slot = P.hint_slot >= 0 ? P.hint_slot : (__ldg(P.ring.head) + P.ring.R - 1) % P.ring.R;
+    hintD = __ldg(P.depth[level] + ((size_t)s * P.ring.R + slot) * npix + p);
+    /* positive floats order like their bit patterns; 0x7f800000 (inf) stands for "no reading" */
+    const unsigned mine = (in_level && hintD > 0.0f) ? __float_as_uint(hintD) : 0x7f800000u;
+    const unsigned gmin = __reduce_min_sync(0xffffffffu, mine);
+    if (!(hintD > 0.0f) && gmin != 0x7f800000u) hintD = __uint_as_float(gmin);
+  }
+  if (!in_level) return;
   if (!miss && lmin < lmax) {
     float lam = lmin;
+    if (hintD > 0.0f) {
+      const float zh = hintD / P.depth_factor;
+      const float start = zh - t.mu * 1.25f, stop = zh + t.mu * 2.0f;
+      if (start > lam) lam = start;
+      if (stop < lmax) lmax = stop; /* the surface fused from this reading is inside this window or nowhere */
+    }
     float fprev = tsdf_nearest(vol, t, __fmaf_rn(lam, dgx, ogx), __fmaf_rn(lam, dgy, ogy), __fmaf_rn(lam, dgz, ogz));
     for (;;) {
       /* inside the truncation band in front of a surface the step shrinks with the distance (never below
@@ -225,31 +256,15 @@ __global__ void __launch_bounds__(256) k_tsdf_raycast(const __grid_constant__ Ra
       const float f = tsdf_nearest(vol, t, __fmaf_rn(lamn, dgx, ogx), __fmaf_rn(lamn, dgy, ogy), __fmaf_rn(lamn, dgz, ogz));
       if (fprev < 0.0f && f > 0.0f) break;
       if (fprev > 0.0f && fprev <= 1.0f && f < 0.0f) {
-        float Ft, Ftn;
-        if (tsdf_trilinear(vol, t, __fmaf_rn(lam, dgx, ogx), __fmaf_rn(lam, dgy, ogy), __fmaf_rn(lam, dgz, ogz), &Ft) &&
-            tsdf_trilinear(vol, t, __fmaf_rn(lamn, dgx, ogx), __fmaf_rn(lamn, dgy, ogy), __fmaf_rn(lamn, dgz, ogz), &Ftn) &&
+        float Ft = 0.0f, Ftn = 0.0f;
+        /* `&` not `&&`: both samples are fetched together (the functions are pure, the result is the same) */
+        if ((tsdf_trilinear(vol, t, __fmaf_rn(lam, dgx, ogx), __fmaf_rn(lam, dgy, ogy), __fmaf_rn(lam, dgz, ogz), &Ft) &
+             tsdf_trilinear(vol, t, __fmaf_rn(lamn, dgx, ogx), __fmaf_rn(lamn, dgy, ogy), __fmaf_rn(lamn, dgz, ogz), &Ftn)) &&
             Ft >= 0.0f && Ftn < 0.0f) {
           const float ls = lam - st * Ft / (Ftn - Ft);
           vz = ls; /* reference viewerModule.c:343-345 with z = the ray parameter */
           vx = ((float)u - g.cx) * ls / g.fx;
           vy = ((float)v - g.cy) * ls / g.fy;
-          const float gx = __fmaf_rn(ls, dgx, ogx), gy = __fmaf_rn(ls, dgy, ogy), gz = __fmaf_rn(ls, dgz, ogz);
-          float xp, xm, yp, ym, zp, zm;
-          if (tsdf_trilinear(vol, t, gx + 1.0f, gy, gz, &xp) && tsdf_trilinear(vol, t, gx - 1.0f, gy, gz, &xm) &&
-              tsdf_trilinear(vol, t, gx, gy + 1.0f, gz, &yp) && tsdf_trilinear(vol, t, gx, gy - 1.0f, gz, &ym) &&
-              tsdf_trilinear(vol, t, gx, gy, gz + 1.0f, &zp) && tsdf_trilinear(vol, t, gx, gy, gz - 1.0f, &zm)) {
-            const float nwx = xp - xm, nwy = yp - ym, nwz = zp - zm;
-            const float ncx = __fmaf_rn(R[0], nwx, __fmaf_rn(R[4], nwy, R[8] * nwz));
-            const float ncy = __fmaf_rn(R[1], nwx, __fmaf_rn(R[5], nwy, R[9] * nwz));
-            const float ncz = __fmaf_rn(R[2], nwx, __fmaf_rn(R[6], nwy, R[10] * nwz));
-            const float len2 = (ncx * ncx + ncy * ncy) + ncz * ncz;
-            if (len2 > 1e-24f) {
-              const float inv = 1.0f / sqrtf(len2);
-              nx = -(ncx * inv);
-              ny = -(ncy * inv);
-              nz = -(ncz * inv);
-            }
-          }
           break;
         }
       }
@@ -257,8 +272,8 @@ __global__ void __launch_bounds__(256) k_tsdf_raycast(const __grid_constant__ Ra
       lam = lamn;
     }
   }
+  /* planes 1.y and 2 (the normal) are completed by k_normals, run over the model maps right after */
   float2* base = P.model[level] + (size_t)s * 3 * npix;
   base[p] = make_float2(vx, vy);
-  base[npix + p] = make_float2(vz, nx);
-  base[2 * npix + p] = make_float2(ny, nz);
+  base[npix + p] = make_float2(vz, YK_N_INVALID);
 }

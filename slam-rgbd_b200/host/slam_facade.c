@@ -26,6 +26,7 @@
 
 #include "SLAM.h"
 #include "youth_host.h"
+#include "youth_model.h"
 
 #define QUEUE_HIGH_WATER 10 /* SLAM.cpp:163 */
 #define QUEUE_LOW_WATER 5   /* SLAM.cpp:165 */
@@ -132,6 +133,21 @@ void initSlamModule(const char* config_file, const char* vocabulary_file) {
     fprintf(stderr, "AlgorithmModule: failed to initialise the CUDA tracker: %s\n", youth_cuda_last_error());
     G.h = NULL;
     return;
+  }
+  {
+    /* YOUTH_SLAM_MODE=model: track against a fused TSDF model instead of the previous frame
+     * (include/youth_model.h) -- what TrackRGBD does with its map, SLAM.cpp:54 */
+    const char* mode = getenv("YOUTH_SLAM_MODE");
+    if (mode && !strcmp(mode, "model")) {
+      youth_tsdf_config tc;
+      youth_tsdf_default_config(&tc);
+      if (!youth_cuda_enable_model(G.h, &tc)) {
+        fprintf(stderr, "AlgorithmModule: cannot enable frame-to-model tracking: %s\n", youth_cuda_last_error());
+        youth_cuda_destroy(G.h);
+        G.h = NULL;
+        return;
+      }
+    }
   }
   G.qcap = QUEUE_HIGH_WATER + 2 + 2 * G.batch; /* queue + one claimed run always fit */
   G.ring = (uint16_t*)youth_cuda_host_alloc(frame_px() * sizeof(uint16_t) * (size_t)G.qcap);

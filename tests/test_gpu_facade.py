@@ -142,6 +142,37 @@ def test_packed_recording_replays_to_the_same_trajectory(pkg, oracle, tmp_path):
     assert len(rows[0].splitlines()) == 70 and rows[0] == rows[1]
 
 
+def test_facade_in_model_mode(pkg, small_seq):
+    """YOUTH_SLAM_MODE=model: the same facade calls, tracking against the fused TSDF model."""
+    from slam_rgbd_b200 import binding as B
+
+    frames, gt = small_seq
+    host = pkg.host_lib()
+    os.environ["YOUTH_SLAM_MODE"] = "model"
+    try:
+        host.youthSlamSetOptions(1, 4)
+        host.initSlamModule(None, None)
+        assert host.isSlamModuleRunning() == 1
+        for i in range(6):
+            assert host.processSlamFrame(frames[i].ctypes.data, None, 640, 480, 33 * i) == 1
+        host.youthSlamDrain()
+        poses = np.empty((6, 12), dtype=np.float32)
+        assert host.youthSlamGetTrajectory(poses.ctypes.data, None, None, 6) == 6
+        host.stopSlamModule()
+    finally:
+        del os.environ["YOUTH_SLAM_MODE"]
+    ref = B.Tracker(pkg.default_config(batch=6))
+    ref.enable_model(pkg.tsdf_config())
+    want = ref.track_batch([frames])[0]
+    ref.close()
+    assert np.array_equal(poses.view(np.uint32), want.view(np.uint32))
+    f2f = make_tracker(pkg, batch=6)
+    other = f2f.track_batch([frames])[0]
+    f2f.close()
+    assert not np.array_equal(poses, other)  # it really is the other tracker
+    assert np.abs(poses[:, [3, 7, 11]] - gt[:, [3, 7, 11]]).max() < 2e-3
+
+
 def test_live_path_reference_chunks_to_tracker(pkg, small_seq):
     """(f)1 live path: frames leave through the REFERENCE's own sendMetadata/sendDataInChunks
     (oracle/_ref, compiled from loggingModule.c) over a real POSIX mq, are reassembled by

@@ -183,10 +183,12 @@ def test_fusion_and_raycast_kernels_bit_exact(pkg, oracle):
         trk.debug_integrate(i, p)
         oracle.tsdf_integrate(ocfg, otcfg, ovol, oracle.OFrame(ocfg, frames[i]).depth(0), p)
         assert np.array_equal(trk.read_volume(), ovol), f"fused volume differs after frame {i}"
-    for p in poses + [pose_of(0.1, -0.2, 0.05, (0.3, -0.1, 0.4))]:
-        trk.debug_raycast(p)
+    cases = [(p, -1) for p in poses + [pose_of(0.1, -0.2, 0.05, (0.3, -0.1, 0.4))]] + [(poses[1], 1), (poses[2], 2)]
+    for p, hint_frame in cases:  # hint_frame >= 0: rays start in front of the depth that frame measured
+        trk.debug_raycast(p, hint_frame=hint_frame)
+        hf = oracle.OFrame(ocfg, frames[hint_frame]) if hint_frame >= 0 else None
         for level in range(3):
-            vm, nm = oracle.tsdf_raycast(ocfg, otcfg, ovol, p, level)
+            vm, nm = oracle.tsdf_raycast(ocfg, otcfg, ovol, p, level, hint=hf.depth(level) if hf else None)
             dv, dn = trk.read_model(B.DBG_VERTEX, level), trk.read_model(B.DBG_NORMAL, level)
             assert np.array_equal(dv.view(np.uint32), vm.view(np.uint32)), f"model vertex map differs at level {level}"
             assert np.array_equal(dn.view(np.uint32), nm.view(np.uint32)), f"model normal map differs at level {level}"
