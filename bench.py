@@ -44,6 +44,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1; the contract is ONE JSON line on stdout.
+    Keep the real stdout for the result and point fd 1 at stderr for everything else."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -223,7 +245,7 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -512,7 +534,7 @@ def run_ours(args):
         "streaming_single_frame": streaming,
         "packed_input": packed_info,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     C.cast(pin_ptr, C.c_void_p)
     trk.lib.youth_cuda_host_free(pin_ptr)
     trk.close()
@@ -538,6 +560,7 @@ def main():
                     help="frame = frame-to-frame (the headline workload), model = frame-to-model (TSDF fusion + ray cast)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
