@@ -6,19 +6,19 @@
  * Byte/integer work, HBM-bound by design: one pass over the raw frame (2 B/pixel in) and one pass
  * over the packed stream (about 0.66 B/pixel out on Astra-shaped depth).
  *
- *   k_yd16_encode   a CTA owns a tile of 256 blocks (8192 pixels): 128-bit loads into shared
- *                   memory; one warp-iteration per block (lane = pixel: ballot mask, previous
- *                   non-zero value by shuffle, zig-zag delta, redux.max for the bit width, shared
- *                   atomicOr bit packing); the tile's payload is assembled per warp in shared
- *                   memory, its place in the stream comes from a decoupled look-back over the
- *                   tile descriptors of the same frame (single pass: the raw frame is read once),
- *                   and it is written with aligned 32-bit stores (funnel shift).  Tiles take
- *                   their index from an atomic ticket, so a tile only ever waits for tiles that
- *                   already started.
+ *   k_yd16_encode   a CTA owns a tile of 256 blocks (8192 pixels): 128-bit loads into a swizzled shared
+ *                   tile; ONE THREAD PER BLOCK (its 64 bytes in 16 registers: mask, first reading and bit
+ *                   width in one pass, codes streamed through a 64-bit accumulator in a second) -- about
+ *                   a fifth of the instructions of a warp-per-block formulation with ballots and
+ *                   shuffles, which ran at 9 % of the HBM roofline; the CTA scans the block sizes, the
+ *                   tile's place in the stream comes from a decoupled look-back over the tile descriptors
+ *                   of the same frame (single pass: the raw frame is read once), and the staged payload
+ *                   is written with aligned 32-bit stores (funnel shift).  Tiles take their index from
+ *                   an atomic ticket, so a tile only ever waits for tiles that already started.
  *   k_yd16_tilesum  per-tile sums of the block-size table (decoder pre-pass, 1 B/block)
- *   k_yd16_decode   tile payload staged in shared memory with aligned 32-bit loads; lane = pixel:
- *                   unaligned bit-field extract by funnel shift, warp inclusive scan of the
- *                   deltas, 128-bit stores of the unpacked tile
+ *   k_yd16_decode   tile payload staged in shared memory with aligned 32-bit loads; one thread per block:
+ *                   unaligned bit-field reads by funnel shift, running sum of the deltas, 128-bit
+ *                   stores of the unpacked tile through the swizzled shared tile
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -29,7 +29,6 @@
 #define YC_TILE_BLOCKS 256
 #define YC_THREADS 256
 #define YC_WARPS 8
-#define YC_REGION (32 * YOUTH_CODEC_MAX_BLOCK_BYTES + 16) /* per-warp payload staging, bytes */
 #define YC_SPIN_LIMIT (1u << 24)
 #define YC_ERR_SPIN 1u
 #define YC_ERR_HEADER 2u
@@ -78,92 +77,151 @@ __device__ __forceinline__ uint32_t yc_rd32(const uint32_t* w, uint32_t pos) {
   return __funnelshift_r(w[pos >> 2], w[(pos >> 2) + 1], (pos & 3u) * 8u);
 }
 
+/* physical 16-byte chunk of logical chunk k (0..3) of block b inside the shared tile: the XOR keeps the
+ * per-thread 16-byte accesses (thread = block, 64-byte stride) free of bank conflicts */
+__device__ __forceinline__ int yc_chunk(int b, int k) { return (b << 2) | (k ^ ((b >> 1) & 3)); }
+
+/* load one tile (256 blocks = 1024 chunks of 8 pixels) of a frame into the swizzled shared tile */
+__device__ __forceinline__ void yc_load_tile(uint4* s_in, const uint16_t* src, int p0, int npix, int vec_ok, int tid) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = tid + YC_THREADS * i;
+    const int px = p0 + 8 * c;
+    uint4 q;
+    if (vec_ok && px + 8 <= npix) {
+      q = ldg_nc_u4(reinterpret_cast<const uint4*>(src + px));
+    } else {
+      uint32_t h[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = (px + j < npix) ? (uint32_t)src[px + j] : 0u;
+      q = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+    }
+    s_in[yc_chunk(c >> 2, c & 3)] = q;
+  }
+}
+
+/* exclusive scan of one value per thread over the CTA (256 threads); *total = sum */
+__device__ __forceinline__ uint32_t yc_block_scan(uint32_t v, uint32_t* s_wsum, int tid, uint32_t* total) {
+  const int lane = tid & 31, warp = tid >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) s_wsum[warp] = inc;
+  __syncthreads();
+  uint32_t base = 0, all = 0;
+#pragma unroll
+  for (int w = 0; w < YC_WARPS; ++w) {
+    const uint32_t x = s_wsum[w];
+    if (w < warp) base += x;
+    all += x;
+  }
+  *total = all;
+  return base + inc - v;
+}
+
+/* One THREAD per block of 32 pixels (256 blocks per CTA): the block's 64 bytes sit in 16 registers, the
+ * mask / first value / bit width come from one pass over them, the CTA scans the 256 block sizes, a second
+ * pass streams the zig-zag codes through a 64-bit accumulator into the block's place in the shared
+ * staging buffer; the tile's place in the stream comes from the decoupled look-back; the whole CTA
+ * copies the staged payload out with aligned 32-bit stores. */
 __global__ void __launch_bounds__(YC_THREADS) k_yd16_encode(const __grid_constant__ YcEncParams P) {
-  __shared__ __align__(16) uint16_t s_px[YC_TILE_BLOCKS * 32];
-  __shared__ __align__(16) uint8_t s_reg[YC_WARPS][YC_REGION];
-  __shared__ uint32_t s_words[YC_WARPS][18];
-  __shared__ uint32_t s_wlen[YC_WARPS];
-  __shared__ uint32_t s_tile, s_excl, s_total;
+  __shared__ __align__(16) uint4 s_in[YC_TILE_BLOCKS * 4];
+  __shared__ __align__(16) uint8_t s_out[YC_TILE_BLOCKS * YOUTH_CODEC_MAX_BLOCK_BYTES + 16];
+  __shared__ uint32_t s_wsum[YC_WARPS];
+  __shared__ uint32_t s_tile, s_excl;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(P.ticket, 1u);
   __syncthreads();
   const int frame = (int)(s_tile / (uint32_t)P.tiles), t = (int)(s_tile % (uint32_t)P.tiles);
   const uint32_t b0 = (uint32_t)t * YC_TILE_BLOCKS;
-  const int p0 = (int)(b0 * 32u);
   const uint16_t* src = P.in + (size_t)frame * P.npix;
   uint8_t* dst_frame = P.out + (size_t)frame * P.out_stride;
+  yc_load_tile(s_in, src, (int)(b0 * 32u), P.npix, P.vec_ok, tid);
+  __syncthreads();
 
-  for (int k = tid; k < YC_TILE_BLOCKS * 4; k += YC_THREADS) {
-    const int px = p0 + k * 8;
-    if (P.vec_ok && px + 8 <= P.npix) {
-      *reinterpret_cast<uint4*>(&s_px[k * 8]) = ldg_nc_u4(reinterpret_cast<const uint4*>(src + px));
-    } else {
+  uint32_t w[16];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s_px[k * 8 + j] = (px + j < P.npix) ? src[px + j] : (uint16_t)0;
-    }
+  for (int k = 0; k < 4; ++k) {
+    const uint4 q = s_in[yc_chunk(tid, k)];
+    w[4 * k] = q.x;
+    w[4 * k + 1] = q.y;
+    w[4 * k + 2] = q.z;
+    w[4 * k + 3] = q.w;
   }
-  __syncthreads();
-
-  const int nblk = (int)min((uint32_t)YC_TILE_BLOCKS, P.nb - b0);
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  uint32_t woff = 0, my_size = 0;
-  uint8_t* reg = s_reg[warp];
-  uint32_t* words = s_words[warp];
+  /* pass 1: mask, first reading, width of the widest code */
+  uint32_t mask = 0, first = 0, prev = 0, zor = 0;
+#pragma unroll
   for (int i = 0; i < 32; ++i) {
-    const int b = warp * 32 + i;
-    if (b >= nblk) break; /* warp-uniform */
-    const uint32_t v = s_px[b * 32 + lane];
-    const uint32_t mask = __ballot_sync(0xffffffffu, v != 0u);
-    uint32_t sz = 4, first = 0, bits = 0;
+    const uint32_t v = (w[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+    const bool nzv = v != 0u;
+    const int d = (int)(int16_t)(uint16_t)(v - prev);
+    const uint32_t z = (uint32_t)((d << 1) ^ (d >> 15)) & 0xffffu;
+    zor |= (nzv && mask != 0u) ? z : 0u;
+    first = (nzv && mask == 0u) ? v : first;
+    prev = nzv ? v : prev;
+    mask |= (nzv ? 1u : 0u) << i;
+  }
+  const uint32_t bits = zor ? 32u - (uint32_t)__clz(zor) : 0u;
+  const uint32_t nbytes = mask ? ((uint32_t)(__popc(mask) - 1) * bits + 7u) >> 3 : 0u;
+  const bool in_frame = b0 + (uint32_t)tid < P.nb;
+  const uint32_t sz = in_frame ? (mask ? 7u + nbytes : 4u) : 0u;
+  if (in_frame) dst_frame[YOUTH_CODEC_HEADER_BYTES + b0 + tid] = (uint8_t)sz; /* block-size table */
+  uint32_t total;
+  const uint32_t off = yc_block_scan(sz, s_wsum, tid, &total);
+
+  /* pass 2: the block's bytes into the staging buffer */
+  if (in_frame) {
+    uint8_t* o = s_out + off;
+    o[0] = (uint8_t)mask;
+    o[1] = (uint8_t)(mask >> 8);
+    o[2] = (uint8_t)(mask >> 16);
+    o[3] = (uint8_t)(mask >> 24);
     if (mask) {
-      const uint32_t lt = mask & lt_mask;
-      const int prev_lane = lt ? 31 - __clz(lt) : lane;
-      const uint32_t pv = __shfl_sync(0xffffffffu, v, prev_lane);
-      const bool has = (v != 0u) && (lt != 0u);
-      const int d = (int)(int16_t)(uint16_t)(v - pv);
-      const uint32_t z = has ? (uint32_t)(uint16_t)((d << 1) ^ (d >> 15)) : 0u;
-      const uint32_t zmax = __reduce_max_sync(0xffffffffu, z);
-      bits = zmax ? 32u - (uint32_t)__clz(zmax) : 0u;
-      first = __shfl_sync(0xffffffffu, v, __ffs(mask) - 1);
-      const uint32_t nbytes = ((uint32_t)(__popc(mask) - 1) * bits + 7u) >> 3;
-      if (lane < 18) words[lane] = 0u;
-      __syncwarp();
-      if (has && bits) {
-        const uint32_t bo = (uint32_t)(__popc(lt) - 1) * bits;
-        const unsigned long long val = (unsigned long long)z << (bo & 31u);
-        atomicOr(&words[bo >> 5], (uint32_t)val);
-        if ((uint32_t)(val >> 32)) atomicOr(&words[(bo >> 5) + 1], (uint32_t)(val >> 32));
+      o[4] = (uint8_t)first;
+      o[5] = (uint8_t)(first >> 8);
+      o[6] = (uint8_t)bits;
+      o += 7;
+      if (bits) {
+        unsigned long long acc = 0ull;
+        uint32_t nb = 0;
+        bool seen = false;
+        prev = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const uint32_t v = (w[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+          if (v != 0u) {
+            if (seen) {
+              const int d = (int)(int16_t)(uint16_t)(v - prev);
+              const uint32_t z = (uint32_t)((d << 1) ^ (d >> 15)) & 0xffffu;
+              acc |= (unsigned long long)z << nb;
+              nb += bits;
+              if (nb >= 8u) { /* nb < 24 here: at most two whole bytes are ready */
+                *o++ = (uint8_t)acc;
+                acc >>= 8;
+                nb -= 8u;
+              }
+              if (nb >= 8u) {
+                *o++ = (uint8_t)acc;
+                acc >>= 8;
+                nb -= 8u;
+              }
+            }
+            seen = true;
+            prev = v;
+          }
+        }
+        if (nb) *o = (uint8_t)acc;
       }
-      __syncwarp();
-      sz = 7u + nbytes;
     }
-    for (uint32_t k = lane; k < sz; k += 32) {
-      uint32_t byte;
-      if (k < 4) byte = mask >> (8 * k);
-      else if (k < 6) byte = first >> (8 * (k - 4));
-      else if (k == 6) byte = bits;
-      else byte = words[(k - 7) >> 2] >> (8 * ((k - 7) & 3));
-      reg[woff + k] = (uint8_t)byte;
-    }
-    __syncwarp();
-    if (lane == i) my_size = sz;
-    woff += sz;
   }
-  /* block-size table: one byte per block */
-  {
-    const uint32_t gb = b0 + (uint32_t)(warp * 32 + lane);
-    if (gb < P.nb) dst_frame[YOUTH_CODEC_HEADER_BYTES + gb] = (uint8_t)my_size;
-  }
-  if (lane == 0) s_wlen[warp] = woff;
-  __syncthreads();
 
   /* where does this tile's payload start?  Decoupled look-back over the tiles of this frame:
    * descriptor = status << 32 | bytes, status 1 = tile aggregate, 2 = inclusive prefix. */
   if (warp == 0) {
-    uint32_t total = 0;
-#pragma unroll
-    for (int w = 0; w < YC_WARPS; ++w) total += s_wlen[w];
     unsigned long long* desc = P.desc + (size_t)frame * P.tiles;
     uint32_t excl = 0;
     if (t > 0) {
@@ -198,30 +256,26 @@ __global__ void __launch_bounds__(YC_THREADS) k_yd16_encode(const __grid_constan
     if (lane == 0) {
       yc_st_volatile(desc + t, (2ull << 32) | (unsigned long long)(excl + total));
       s_excl = excl;
-      s_total = total;
     }
   }
-  __syncthreads();
+  __syncthreads(); /* staging complete, s_excl known */
 
-  /* write this warp's payload: head bytes up to 4-byte alignment, aligned words through a funnel
-   * shift of the (differently aligned) shared staging, tail bytes */
+  /* copy out: head bytes up to 4-byte alignment, aligned words through a funnel shift of the
+   * (differently aligned) staging buffer, tail bytes */
   {
-    uint32_t wo = 0;
-    for (int w = 0; w < warp; ++w) wo += s_wlen[w];
-    uint8_t* dst = dst_frame + YOUTH_CODEC_HEADER_BYTES + P.nb + s_excl + wo;
-    const uint32_t len = woff;
+    uint8_t* dst = dst_frame + YOUTH_CODEC_HEADER_BYTES + P.nb + s_excl;
     uint32_t head = (uint32_t)((4u - ((uint32_t)(uintptr_t)dst & 3u)) & 3u);
-    if (head > len) head = len;
-    if ((uint32_t)lane < head) dst[lane] = reg[lane];
-    const uint32_t nwords = (len - head) >> 2;
-    const uint32_t* regw = reinterpret_cast<const uint32_t*>(reg);
+    if (head > total) head = total;
+    if ((uint32_t)tid < head) dst[tid] = s_out[tid];
+    const uint32_t nwords = (total - head) >> 2;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s_out);
     uint32_t* dstw = reinterpret_cast<uint32_t*>(dst + head);
-    for (uint32_t k = lane; k < nwords; k += 32) dstw[k] = yc_rd32(regw, head + 4u * k);
+    for (uint32_t k = tid; k < nwords; k += YC_THREADS) dstw[k] = yc_rd32(sw, head + 4u * k);
     const uint32_t done_bytes = head + 4u * nwords;
-    if ((uint32_t)lane < len - done_bytes) dst[done_bytes + lane] = reg[done_bytes + lane];
+    if ((uint32_t)tid < total - done_bytes) dst[done_bytes + tid] = s_out[done_bytes + tid];
   }
   if (t == P.tiles - 1 && tid == 0) { /* the last tile knows the payload size: frame header */
-    const uint32_t pay = s_excl + s_total;
+    const uint32_t pay = s_excl + total;
     uint32_t* hd = reinterpret_cast<uint32_t*>(dst_frame); /* frames start 16-byte aligned */
     hd[0] = YOUTH_CODEC_MAGIC;
     hd[1] = (uint32_t)P.width | ((uint32_t)P.height << 16);
@@ -251,11 +305,12 @@ __global__ void __launch_bounds__(YC_THREADS) k_yd16_tilesum(const __grid_consta
 
 #define YC_STAGE_WORDS ((YC_TILE_BLOCKS * YOUTH_CODEC_MAX_BLOCK_BYTES + 3) / 4 + 4)
 
+/* One THREAD per block: the tile's payload is staged in shared memory with aligned 32-bit loads, every
+ * thread walks its block's codes with unaligned 32-bit reads (funnel shift of two staged words) and a
+ * running sum, the unpacked tile leaves through the swizzled shared tile with 128-bit stores. */
 __global__ void __launch_bounds__(YC_THREADS) k_yd16_decode(const __grid_constant__ YcDecParams P) {
-  __shared__ __align__(16) uint16_t s_px[YC_TILE_BLOCKS * 32];
+  __shared__ __align__(16) uint4 s_px[YC_TILE_BLOCKS * 4];
   __shared__ uint32_t s_stage[YC_STAGE_WORDS];
-  __shared__ uint32_t s_off[YC_TILE_BLOCKS];
-  __shared__ uint8_t s_sz[YC_TILE_BLOCKS];
   __shared__ uint32_t s_wsum[YC_WARPS];
   __shared__ uint32_t s_base;
   __shared__ int s_bad;
@@ -303,22 +358,11 @@ __global__ void __launch_bounds__(YC_THREADS) k_yd16_decode(const __grid_constan
     }
   }
   /* block offsets inside the tile: exclusive scan of the 256 sizes */
-  const uint32_t gb = b0 + (uint32_t)tid;
-  const uint32_t mysz = gb < P.nb ? base[YOUTH_CODEC_HEADER_BYTES + gb] : 0u;
-  uint32_t inc = mysz;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-    if (lane >= d) inc += o;
-  }
-  if (lane == 31) s_wsum[warp] = inc;
-  __syncthreads();
+  const bool in_frame = b0 + (uint32_t)tid < P.nb;
+  const uint32_t sz = in_frame ? base[YOUTH_CODEC_HEADER_BYTES + b0 + tid] : 0u;
+  uint32_t total;
+  const uint32_t off = yc_block_scan(sz, s_wsum, tid, &total); /* contains a __syncthreads: s_base / s_bad are visible */
   if (s_bad) return;
-  uint32_t wbase = 0;
-  for (int w = 0; w < warp; ++w) wbase += s_wsum[w];
-  s_off[tid] = wbase + inc - mysz;
-  s_sz[tid] = (uint8_t)mysz;
-  const uint32_t total = tsum[t];
   if (total > (uint32_t)(YC_TILE_BLOCKS * YOUTH_CODEC_MAX_BLOCK_BYTES)) { /* a legal tile never is */
     if (tid == 0) atomicOr(P.err, YC_ERR_SIZES);
     return;
@@ -331,16 +375,11 @@ __global__ void __launch_bounds__(YC_THREADS) k_yd16_decode(const __grid_constan
   for (uint32_t k = tid; k < nwords + 2u; k += YC_THREADS) s_stage[k] = k < nwords ? __ldg(a0 + k) : 0u;
   __syncthreads();
 
-  const int nblk = (int)min((uint32_t)YC_TILE_BLOCKS, P.nb - b0);
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  for (int i = 0; i < 32; ++i) {
-    const int b = warp * 32 + i;
-    if (b >= nblk) { /* tile tail beyond the frame: keep the shared tile defined */
-      s_px[b * 32 + lane] = 0;
-      continue;
-    }
-    const uint32_t o = shift + s_off[b], sz = s_sz[b];
-    uint32_t val = 0;
+  uint32_t w[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) w[k] = 0u;
+  if (in_frame) {
+    const uint32_t o = shift + off;
     bool bad = sz < 4u;
     if (!bad) {
       const uint32_t mask = yc_rd32(s_stage, o);
@@ -353,38 +392,44 @@ __global__ void __launch_bounds__(YC_THREADS) k_yd16_decode(const __grid_constan
         const uint32_t first = fb & 0xffffu, bits = (fb >> 16) & 0xffu;
         bad = bits > 16u || sz != 7u + (((uint32_t)(__popc(mask) - 1) * bits + 7u) >> 3);
         if (!bad) {
-          const uint32_t lt = mask & lt_mask;
-          const bool set = (mask >> lane) & 1u;
-          uint32_t delta = 0;
-          if (set && lt && bits) {
-            const uint32_t bo = (uint32_t)(__popc(lt) - 1) * bits;
-            const uint32_t x = yc_rd32(s_stage, o + 7u + (bo >> 3));
-            const uint32_t z = (x >> (bo & 7u)) & ((1u << bits) - 1u);
-            delta = (z >> 1) ^ (0u - (z & 1u)); /* un-zig-zag; only the low 16 bits matter */
-          }
+          const uint32_t vmask = (1u << bits) - 1u;
+          uint32_t cur = first, bitpos = (o + 7u) * 8u;
+          bool seen = false;
 #pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xffffffffu, delta, d);
-            if (lane >= d) delta += up;
+          for (int i = 0; i < 32; ++i) {
+            if ((mask >> i) & 1u) {
+              if (seen && bits) {
+                const uint32_t x = yc_rd32(s_stage, bitpos >> 3);
+                const uint32_t z = (x >> (bitpos & 7u)) & vmask;
+                cur = (cur + ((z >> 1) ^ (0u - (z & 1u)))) & 0xffffu; /* un-zig-zag, modulo 2^16 */
+                bitpos += bits;
+              }
+              seen = true;
+              w[i >> 1] |= cur << (16 * (i & 1));
+            }
           }
-          val = set ? ((first + delta) & 0xffffu) : 0u;
         }
       }
     }
-    if (bad && lane == 0) atomicOr(P.err, YC_ERR_BLOCK);
-    s_px[b * 32 + lane] = (uint16_t)val;
+    if (bad) atomicOr(P.err, YC_ERR_BLOCK);
   }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) s_px[yc_chunk(tid, k)] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
   __syncthreads();
   uint16_t* dst = P.out + (size_t)frame * P.npix;
   const int p0 = (int)(b0 * 32u);
-  for (int k = tid; k < YC_TILE_BLOCKS * 4; k += YC_THREADS) {
-    const int px = p0 + k * 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = tid + YC_THREADS * i;
+    const int px = p0 + 8 * c;
+    const uint4 q = s_px[yc_chunk(c >> 2, c & 3)];
     if (P.vec_ok && px + 8 <= P.npix) {
-      *reinterpret_cast<uint4*>(dst + px) = *reinterpret_cast<const uint4*>(&s_px[k * 8]);
+      *reinterpret_cast<uint4*>(dst + px) = q;
     } else {
+      const uint32_t h[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (px + j < P.npix) dst[px + j] = s_px[k * 8 + j];
+        if (px + j < P.npix) dst[px + j] = (uint16_t)(h[j >> 1] >> (16 * (j & 1)));
     }
   }
 }

@@ -28,6 +28,7 @@
 #define YK_MAX_CHUNKS 64
 #define YK_GRAPH_MAX_N 8   /* groups of at most this many frames per stream run as one captured CUDA graph */
 #define YK_GRAPH_SLOTS (2 * YK_GRAPH_MAX_N)
+#define YK_ICP_LAST_CTA_MAX_CTAS 444 /* one wave of the 152-register variant: 3 CTAs on each of 148 SMs */
 
 /* ------------------------------------------------------------------ errors */
 
@@ -412,7 +413,12 @@ template <bool DEBUG>
 static void launch_icp(youth_cuda_handle* h, const IcpParams& ip, int pairs, int level) {
   ProfScope ps(h, YOUTH_PROF_ICP0 + level);
   const dim3 grid((h->nruns[level] + YK_ICP_WARPS - 1) / YK_ICP_WARPS, pairs);
-  k_icp<DEBUG><<<grid, 32 * YK_ICP_WARPS, 0, h->stream>>>(ip);
+  /* few pairs per launch (live / frame-to-model): the latency of the tail matters, share it between the
+   * warps of the last CTA; many pairs: no block barrier, the tails of different pairs overlap anyway */
+  if (!DEBUG && (long long)grid.x * pairs <= YK_ICP_LAST_CTA_MAX_CTAS)
+    k_icp<false, true><<<grid, 32 * YK_ICP_WARPS, 0, h->stream>>>(ip);
+  else
+    k_icp<DEBUG, false><<<grid, 32 * YK_ICP_WARPS, 0, h->stream>>>(ip);
 }
 
 static IcpParams icp_params(const youth_cuda_handle* h, int level, const RingGeom& ring) {

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--levels", type=int, default=3)
     ap.add_argument("--ppt", type=int, default=64)
+    ap.add_argument("--model", action="store_true", help="frame-to-model tracking (TSDF fusion + ray cast)")
     args = ap.parse_args()
     import torch
 
@@ -34,6 +35,8 @@ def main():
                              fx=570.3 * args.width / 640, fy=570.3 * args.width / 640, cx=args.width / 2,
                              cy=args.height / 2)
     trk = B.Tracker(cfg)
+    if args.model:
+        trk.enable_model(pkg.tsdf_config())
     seqs = [pkg.synth_sequence(n, args.width, args.height, sequence=s) for s in range(args.streams)]
     dev = [torch.from_numpy(s.view(np.int16)).cuda() for s in seqs]
     fb = args.width * args.height * 2
