@@ -86,7 +86,8 @@ uint64_t youth_codec_launch_count(const youth_codec* c);
  * device and unpacked there, straight into the tracker's raw landing zone (a third of the PCIe
  * traffic of raw frames).  Host buffers must stay valid until the call returns (it returns after
  * the copies were enqueued from pageable memory, or when poses_out is non-NULL after the
- * group finished; pinned inputs follow the YOUTH_MEM_HOST_PINNED rule). */
+ * group finished; pinned inputs follow the YOUTH_MEM_HOST_PINNED rule).  On a frame-to-model handle
+ * (youth_model.h) the group is unpacked as a whole and then tracked frame after frame. */
 int youth_cuda_track_batch_packed(youth_cuda_handle* h, const uint8_t* const* streams,
                                   const uint64_t* const* offsets, int n_frames, int mem_kind,
                                   const uint32_t* timestamps_ms, float* poses_out);

@@ -865,7 +865,6 @@ extern "C" int youth_cuda_track_batch_packed(youth_cuda_handle* h, const uint8_t
   if (!h || !streams || !offsets) return fail("null argument");
   if (n_frames < 1 || n_frames > h->B) return fail("n_frames must be 1..batch (%d)", h->B);
   if (mem_kind != YOUTH_MEM_HOST && mem_kind != YOUTH_MEM_HOST_PINNED) return fail("packed input must be host memory");
-  if (h->m.on) return fail("packed input is not available in frame-to-model mode (unpack with youth_codec_decode)");
   for (int s = 0; s < h->S; ++s) {
     if (!streams[s] || !offsets[s]) return fail("streams[%d] / offsets[%d] is NULL", s, s);
     if (h->h_count[s] + n_frames > h->cfg.traj_capacity) return fail("trajectory capacity (%d) exceeded", h->cfg.traj_capacity);
@@ -885,6 +884,34 @@ extern "C" int youth_cuda_track_batch_packed(youth_cuda_handle* h, const uint8_t
       if (offsets[s][i + 1] < offsets[s][i]) return fail("offsets must be non-decreasing");
       if (!codec_check_header(c, streams[s] + offsets[s][i], offsets[s][i + 1] - offsets[s][i], s * n_frames + i)) return 0;
     }
+  if (h->m.on) {
+    /* frame-to-model: a chain of single frames.  Unpack the whole group into the codec's raw buffer on the
+     * tracking stream, then run the chain from device memory. */
+    CU(cudaStreamSynchronize(h->stream)); /* the previous group no longer reads the staging buffers */
+    unsigned long long* O = h->pk_h_off[0];
+    unsigned long long base = 0;
+    for (int s = 0; s < h->S; ++s) {
+      for (int i = 0; i < n_frames; ++i) O[(size_t)s * n_frames + i] = base + (offsets[s][i] - offsets[s][0]);
+      base += offsets[s][n_frames] - offsets[s][0];
+    }
+    O[(size_t)h->S * n_frames] = base;
+    if (base > (unsigned long long)h->P * c->stride) return fail("packed group larger than the context");
+    const size_t frame_px = (size_t)h->cfg.width * h->cfg.height;
+    CU(cudaMemcpyAsync(h->pk_d_off[0], O, sizeof(unsigned long long) * ((size_t)h->S * n_frames + 1), cudaMemcpyHostToDevice,
+                       h->stream));
+    for (int s = 0; s < h->S; ++s)
+      CU(cudaMemcpyAsync(c->d_packed + O[(size_t)s * n_frames], streams[s] + offsets[s][0],
+                         (size_t)(offsets[s][n_frames] - offsets[s][0]), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(c->d_err, 0, sizeof(unsigned int), h->stream));
+    h->launches += 2;
+    if (!codec_enqueue_decode(c, h->stream, c->d_packed, h->pk_d_off[0], c->d_tile_sum, h->S * n_frames, c->d_raw)) return 0;
+    CU(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    const uint16_t* dev[YK_MAX_STREAMS];
+    for (int s = 0; s < h->S; ++s) dev[s] = c->d_raw + (size_t)s * n_frames * frame_px;
+    if (!track_batch_model(h, dev, n_frames, YOUTH_MEM_DEVICE, timestamps_ms, poses_out)) return 0;
+    if (poses_out && *c->h_err) return fail("malformed YD16 stream (device check 0x%x); reset the tracker", *c->h_err);
+    return 1;
+  }
   const int k = h->raw_turn;
   h->raw_turn ^= 1;
   if (h->raw_used[k]) CU(cudaEventSynchronize(h->raw_free[k])); /* pk_h_off[k] and raw[k] of two calls ago are free */
@@ -1170,6 +1197,7 @@ extern "C" int youth_cuda_debug_icp(youth_cuda_handle* h, int stream, int frame,
   ip.dbg_prev_slot = prev;
   ip.dbg_stream = stream;
   ip.do_solve = 0;
+  ip.model = NULL; /* always frame `frame` against frame - 1, also on a frame-to-model handle */
   launch_icp<true>(h, ip, 1, level);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(sums_out, h->sums, sizeof(double) * 32, cudaMemcpyDeviceToHost, h->stream));

@@ -264,8 +264,13 @@ def test_model_mode_properties_full_size(pkg, oracle):
     em = np.linalg.norm(p0.reshape(-1, 3, 4)[:, :, 3] - gt.reshape(-1, 3, 4)[:, :, 3], axis=1)
     ef = np.linalg.norm(pf.reshape(-1, 3, 4)[:, :, 3] - gt.reshape(-1, 3, 4)[:, :, 3], axis=1)
     assert em.max() < 0.01 and em[-1] < ef[-1]
-    # packed input is refused in this mode, loudly
-    with pytest.raises(RuntimeError):
-        t2 = B.Tracker(pkg.default_config(batch=2))
-        t2.enable_model(tcfg)
-        t2.track_batch_packed([np.zeros(16, np.uint8)], [np.zeros(3, np.uint64)], 2)
+    # YD16-packed input feeds the same chain (unpacked on the device)
+    cd = pkg.Codec(640, 480, max_frames=30)
+    packed, offs = cd.encode(seqs[0][:30])
+    cd.close()
+    t2 = B.Tracker(pkg.default_config(batch=20, traj_capacity=32))
+    t2.enable_model(tcfg)
+    a = t2.track_batch_packed([packed], [offs[:21].copy()], 20)[0]
+    b = t2.track_batch_packed([packed], [offs[20:].copy()], 10)[0]
+    t2.close()
+    assert np.array_equal(np.concatenate([a, b]).view(np.uint32), p0[:30].view(np.uint32))
