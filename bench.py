@@ -139,7 +139,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------- CPU oracle arm
 
 
-def cpu_oracle_fps(frames, cfg_product, threads, frames_per_thread, fast=True):
+def cpu_oracle_fps(frames, cfg_product, threads, frames_per_thread, fast=True, tsdf_cfg=None):
     """Track `threads` independent sub-sequences of `frames_per_thread` frames in parallel
     (same partitioning as the GPU's independent frame pairs).  Returns (fps, seconds, kind)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -147,6 +147,9 @@ def cpu_oracle_fps(frames, cfg_product, threads, frames_per_thread, fast=True):
 
     ocfg = O.config_from(cfg_product)
     use_fast = False
+    if tsdf_cfg is not None:  # frame-to-model statement: parity build only
+        fast = False
+        otcfg = O.tsdf_config_from(tsdf_cfg)
     if fast:
         try:
             O.lib(fast=True)
@@ -161,8 +164,11 @@ def cpu_oracle_fps(frames, cfg_product, threads, frames_per_thread, fast=True):
     secs = [0.0] * threads
 
     def work(i):
-        _, _, s = O.track_sequence(ocfg, chunks[i], fast=use_fast)
-        secs[i] = s
+        if tsdf_cfg is not None:
+            O.track_sequence_model(ocfg, otcfg, chunks[i])
+        else:
+            _, _, s = O.track_sequence(ocfg, chunks[i], fast=use_fast)
+            secs[i] = s
 
     t0 = time.perf_counter()
     ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
@@ -173,6 +179,33 @@ def cpu_oracle_fps(frames, cfg_product, threads, frames_per_thread, fast=True):
     wall = time.perf_counter() - t0
     tracked = threads * frames_per_thread
     return tracked / wall, wall, ("-O3 -mavx2 -mfma build" if use_fast else "-O2 -ffp-contract=off parity build")
+
+
+def bind_to_gpu_numa_node(local):
+    """Run this rank (and so first-touch its pinned host buffers) on the CPUs of the NUMA node the GPU hangs
+    off: with one rank per GPU the H2D streams of 8 GPUs otherwise cross the socket interconnect.
+    Best effort: returns a description, never raises."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return f"gpu {bdf}: no NUMA node reported"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return f"gpu {bdf}: node {node} has no CPU in this process's affinity mask"
+        os.sched_setaffinity(0, allowed)
+        return f"gpu {bdf}: bound to NUMA node {node} ({len(allowed)} CPUs)"
+    except Exception as e:  # no sysfs, old torch, restricted container ...
+        return f"not bound ({type(e).__name__}: {e})"
 
 
 def host_threads():
@@ -206,6 +239,7 @@ def base_config_dict(args, n_gpus):
         "icp_ppt": getattr(args, "ppt", 0) or 64,
         "sequences_per_gpu": spg,
         "partition": f"{n_gpus * spg} independent sequence(s), {spg} per GPU, no data-path collective",
+        "host_placement": getattr(args, "numa_note", "n/a"),
         "l2": f"inputs ({raw_mb:.0f} MB raw depth per step) exceed the 126 MB L2 and are streamed once per step; "
               "no explicit flush",
     }
@@ -263,6 +297,9 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the tracking path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 and not args.no_numa else "single rank: not bound"
+    log(f"[rank {rank}] {numa}")
+    args.numa_note = numa
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -503,9 +540,17 @@ def run_ours(args):
 
     threads = max(1, min(host_threads(), 32))
     fpt = max(3, int(61 * (W * H) / (Wd * Hd)))  # 60 frame pairs per thread at 640x480: about 10-15 s of CPU work
-    cpu_fps, cpu_wall, cpu_kind = cpu_oracle_fps(frames[0], cfg, threads, fpt)
-    cpu1_fps, _, _ = cpu_oracle_fps(frames[0], cfg, 1, max(3, fpt // 6))               # one thread, speed build
-    cpu1p_fps, _, _ = cpu_oracle_fps(frames[0], cfg, 1, max(3, fpt // 6), fast=False)  # one thread, parity build
+    if args.mode == "model":  # the frame-to-model statement (fusion + ray cast on top of the same ICP), parity build
+        fpt = 12
+        mt = pkg.tsdf_config()
+        cpu_fps, cpu_wall, cpu_kind = cpu_oracle_fps(frames[0], cfg, threads, fpt, tsdf_cfg=mt)
+        cpu_kind = "frame-to-model statement, " + cpu_kind
+        cpu1_fps, _, _ = cpu_oracle_fps(frames[0], cfg, 1, 4, tsdf_cfg=mt)
+        cpu1p_fps = cpu1_fps
+    else:
+        cpu_fps, cpu_wall, cpu_kind = cpu_oracle_fps(frames[0], cfg, threads, fpt)
+        cpu1_fps, _, _ = cpu_oracle_fps(frames[0], cfg, 1, max(3, fpt // 6))               # one thread, speed build
+        cpu1p_fps, _, _ = cpu_oracle_fps(frames[0], cfg, 1, max(3, fpt // 6), fast=False)  # one thread, parity build
 
     line = {
         "metric": "icp_tracked_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
@@ -556,6 +601,7 @@ def main():
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--levels", type=int, default=3)
     ap.add_argument("--no-packed", action="store_true", help="skip the YD16 packed-input arm")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind ranks to their GPU's NUMA node")
     ap.add_argument("--mode", default="frame", choices=["frame", "model"],
                     help="frame = frame-to-frame (the headline workload), model = frame-to-model (TSDF fusion + ray cast)")
     args = ap.parse_args()
