@@ -216,6 +216,34 @@ def test_model_trajectory_bit_exact_small(pkg, oracle):
 
 
 @pytest.mark.gpu
+def test_model_survives_empty_and_partly_blind_frames(pkg, oracle):
+    """a frame without readings is flagged LOST, keeps the pose, is NOT fused; a half-blind frame still tracks;
+    the chain stays bit-identical to the CPU statement throughout"""
+    from slam_rgbd_b200 import binding as B
+
+    trk, ocfg, otcfg = make_model_tracker(pkg, oracle, batch=4, traj_capacity=16)
+    frames = pkg.synth_sequence(10, 160, 120).copy()
+    frames[4] = 0                 # sensor drop-out
+    frames[7][:, 80:] = 0         # right half blind
+    frames[8][:60] = 65535        # top half out of range (> depth_max)
+    got = np.concatenate([trk.track_batch([frames[a:a + 4]])[0] for a in range(0, 10, 4)])
+    want, st = oracle.track_sequence_model(ocfg, otcfg, frames)
+    _, _, dst = trk.trajectory()
+    assert np.array_equal(dst, st) and st[4] == B.STATUS_LOST and (st[[1, 2, 3, 5, 6, 7, 9]] == 0).all()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(got[4], got[3])  # pose kept
+    # the volume after the run equals the statement's (so the empty frame was not fused on either side)
+    vol = oracle.tsdf_new(otcfg)
+    for i in range(10):
+        if st[i] & B.STATUS_LOST:
+            continue
+        fr = oracle.OFrame(ocfg, frames[i])
+        oracle.tsdf_integrate(ocfg, otcfg, vol, fr.depth(0), want[i])
+    assert np.array_equal(trk.read_volume(), vol)
+    trk.close()
+
+
+@pytest.mark.gpu
 def test_model_trajectory_bit_exact_full_size(pkg, oracle):
     trk, ocfg, otcfg = make_model_tracker(pkg, oracle, small=False, batch=4, traj_capacity=16)
     frames = pkg.synth_sequence(4)
