@@ -629,7 +629,7 @@ static int enqueue_integrate(youth_cuda_handle* h, int s0, int ns, int slot, boo
   memset(&p, 0, sizeof(p));
   p.vol = h->m.vol;
   p.t = h->m.geom;
-  p.depth0 = h->depth[0];
+  p.maps0 = h->maps[0];
   p.g = h->lv[0];
   p.ring = ring_of(h, 1);
   p.world_f = h->m.world_f;

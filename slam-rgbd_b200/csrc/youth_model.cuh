@@ -30,6 +30,9 @@
 #define YM_INV_SCALE (1.0f / 32767.0f)
 #define YM_UNKNOWN 2.0f
 #define YM_ZCHUNK 16
+#ifndef YM_RAYCAST_MIN_BLOCKS
+#define YM_RAYCAST_MIN_BLOCKS 6 /* 40 registers: measured 8 % faster than 64 registers at 4 CTAs per SM */
+#endif
 
 struct TsdfGeom {
   int dx, dy, dz;
@@ -43,7 +46,8 @@ struct TsdfGeom {
 struct IntegrateParams {
   short2* vol;                 /* [S][dz][dy][dx] */
   TsdfGeom t;
-  const float* depth0;         /* [S][R][npix0] level-0 depth of the ring */
+  const float2* maps0;         /* [S][R][3][npix0] level-0 map planes of the ring: plane 1 .x is z = D / depth_factor,
+                                  computed by stage 2 with the very expression the specification uses here */
   LevelGeom g;                 /* level 0 */
   RingGeom ring;
   const float* world_f;        /* [S][12] camera-to-world */
@@ -78,9 +82,9 @@ __global__ void __launch_bounds__(256) k_tsdf_integrate(const __grid_constant__ 
   const int s = P.stream0 + blockIdx.z / zchunks, zc = blockIdx.z % zchunks;
   if (P.last_status != nullptr && (P.last_status[s] & YOUTH_STATUS_LOST)) return;
   const int ix = blockIdx.x * 32 + (threadIdx.x & 31), iy = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (ix >= P.t.dx || iy >= P.t.dy) return;
   const int slot = P.slot >= 0 ? P.slot : (__ldg(P.ring.head) + P.ring.R - 1) % P.ring.R;
-  const float* __restrict__ depth = P.depth0 + ((size_t)s * P.ring.R + slot) * (size_t)(P.g.w * P.g.h);
+  const size_t npix0 = (size_t)(P.g.w * P.g.h);
+  const float2* __restrict__ zplane = P.maps0 + (((size_t)s * P.ring.R + slot) * 3 + 1) * npix0;
   const float* T = P.world_f + s * 12;
   /* world -> camera: R^T and -R^T t */
   float Ri[9], ti[3];
@@ -90,6 +94,35 @@ __global__ void __launch_bounds__(256) k_tsdf_integrate(const __grid_constant__ 
     for (int j = 0; j < 3; ++j) Ri[3 * i + j] = __ldg(T + 4 * j + i);
     ti[i] = -__fmaf_rn(__ldg(T + i), __ldg(T + 3), __fmaf_rn(__ldg(T + 4 + i), __ldg(T + 7), __ldg(T + 8 + i) * __ldg(T + 11)));
   }
+  /* Conservative frustum culling of the CTA's box of voxels (32 x 8 x 16): its eight corners lie half a
+   * voxel outside the outermost voxel centres; when all eight are on the outer side of one frustum plane
+   * (the side planes pass through the camera centre: n . p < 0 with n = (fx, 0, cx+1/2) etc.) no voxel of
+   * the box can pass the per-voxel image test below, so skipping the box changes nothing.  The half
+   * voxel (>= 1 pixel at any depth inside the volume) dwarfs the rounding differences between this test and
+   * the per-voxel arithmetic. */
+  {
+    __shared__ int s_keep;
+    if (threadIdx.x == 0) s_keep = 0;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      const int cx0 = blockIdx.x * 32, cy0 = blockIdx.y * 8, cz0 = zc * YM_ZCHUNK;
+      const float bx = P.t.ox + (float)(cx0 + ((threadIdx.x & 1) ? 32 : 0)) * P.t.vs;
+      const float by = P.t.oy + (float)(cy0 + ((threadIdx.x & 2) ? 8 : 0)) * P.t.vs;
+      const float bz = P.t.oz + (float)(cz0 + ((threadIdx.x & 4) ? YM_ZCHUNK : 0)) * P.t.vs;
+      const float qx = Ri[0] * bx + Ri[1] * by + Ri[2] * bz + ti[0];
+      const float qy = Ri[3] * bx + Ri[4] * by + Ri[5] * bz + ti[1];
+      const float qz = Ri[6] * bx + Ri[7] * by + Ri[8] * bz + ti[2];
+      const float hu = P.g.fx * qx + P.g.cxh * qz, hv = P.g.fy * qy + P.g.cyh * qz; /* u * z, v * z */
+      const unsigned m = 0xffu;
+      const bool out_near = __all_sync(m, qz <= 0.0f);
+      const bool out_left = __all_sync(m, hu < 0.0f), out_right = __all_sync(m, hu >= (float)P.g.w * qz && qz > 0.0f);
+      const bool out_top = __all_sync(m, hv < 0.0f), out_bottom = __all_sync(m, hv >= (float)P.g.h * qz && qz > 0.0f);
+      if (threadIdx.x == 0 && !(out_near || out_left || out_right || out_top || out_bottom)) s_keep = 1;
+    }
+    __syncthreads();
+    if (!s_keep) return;
+  }
+  if (ix >= P.t.dx || iy >= P.t.dy) return;
   const float wx = __fmaf_rn((float)ix + 0.5f, P.t.vs, P.t.ox);
   const float wy = __fmaf_rn((float)iy + 0.5f, P.t.vs, P.t.oy);
   /* the x / y part of the transform is shared by the column; the nesting order of the specification is
@@ -110,14 +143,22 @@ __global__ void __launch_bounds__(256) k_tsdf_integrate(const __grid_constant__ 
     const float ur = __fmaf_rn(px * P.g.fx, iz1, P.g.cxh);
     const float vr = __fmaf_rn(py * P.g.fy, iz1, P.g.cyh);
     if (!(ur >= 0.0f && ur < (float)P.g.w && vr >= 0.0f && vr < (float)P.g.h)) continue;
-    const float D = __ldg(depth + __float2int_rz(vr) * P.g.w + __float2int_rz(ur));
-    if (!(D > 0.0f)) continue;
-    const float sdf = D / P.depth_factor - pz;
+    /* z of the measured vertex = D / depth_factor (0 where the pixel has no reading) */
+    const float zm = __ldg(reinterpret_cast<const float*>(zplane + __float2int_rz(vr) * P.g.w + __float2int_rz(ur)));
+    if (!(zm > 0.0f)) continue;
+    const float sdf = zm - pz;
     if (!(sdf >= -P.t.mu)) continue;
     float f = sdf / P.t.mu;
     if (f > 1.0f) f = 1.0f;
     short2* vp = col + (size_t)iz * zstride;
     const short2 v = *vp;
+    if (f == 1.0f && v.x == 32767) {
+      /* free space seen as free space again: (F W + 1) / (W + 1) with F = 32767 * fl(1/32767) differs from 1 by
+       * less than 1e-6, so the stored value stays 32767 -- only the weight moves (and not at all once it
+       * has reached the cap): the same result as the arithmetic below, without it */
+      if (v.y < P.t.maxw) *vp = make_short2((short)32767, (short)(v.y + 1));
+      continue;
+    }
     const float F = (float)v.x * YM_INV_SCALE, W = (float)v.y;
     const float Fn = (F * W + f) / (W + 1.0f);
     const int wn = v.y + 1 > P.t.maxw ? P.t.maxw : v.y + 1;
@@ -169,7 +210,7 @@ __device__ __forceinline__ bool tsdf_trilinear(const short2* __restrict__ vol, c
   return true;
 }
 
-__global__ void __launch_bounds__(256) k_tsdf_raycast(const __grid_constant__ RaycastParams P) {
+__global__ void __launch_bounds__(256, YM_RAYCAST_MIN_BLOCKS) k_tsdf_raycast(const __grid_constant__ RaycastParams P) {
   int p = blockIdx.x * 256 + threadIdx.x;
   const int s = P.stream0 + blockIdx.y;
   /* levels are laid out one after the other, each padded to a multiple of 32 pixels, so a warp never

@@ -230,3 +230,36 @@ def test_parity_across_configurations(pkg, oracle, w, h, levels, extra, noise):
     if extra.get("min_inliers", 0) > 50000:
         assert list(st) == [1, 2, 2]
     trk.close()
+
+
+def test_independent_handles_from_two_threads(pkg, small_seq):
+    """handles are independent (include/youth_cuda.h, Threading): two trackers driven concurrently from two
+    host threads give the bits of a tracker driven alone"""
+    import threading
+
+    from slam_rgbd_b200 import binding as B
+
+    frames, _ = small_seq
+    alone = B.Tracker(pkg.default_config(batch=6))
+    want = alone.track_batch([frames])[0]
+    alone.close()
+    out = [None, None]
+
+    def work(k):
+        t = B.Tracker(pkg.default_config(batch=3 if k else 2))
+        n = 3 if k else 2
+        res = []
+        for rep in range(4):
+            t.reset()
+            res = [t.track_batch([frames[a:a + n]])[0] for a in range(0, 6, n)]
+        out[k] = np.concatenate(res)
+        t.close()
+
+    ths = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join(timeout=120)
+    assert all(not th.is_alive() for th in ths)
+    for k in range(2):
+        assert np.array_equal(out[k].view(np.uint32), want.view(np.uint32))
