@@ -57,6 +57,11 @@ int youth_cuda_enable_model(youth_cuda_handle* h, const youth_tsdf_config* cfg);
 /* 1 when the handle tracks against a model */
 int youth_cuda_model_enabled(const youth_cuda_handle* h);
 
+/* Size of the map of sequence `stream`: observed voxels whose tsdf changes sign towards an observed +x, +y
+ * or +z neighbour -- the voxels the fused surface passes through; the dense counterpart of
+ * `GetAllMapPoints().size()` (reference SLAM.cpp:212-217).  Blocking; -1 on error. */
+long long youth_cuda_model_surface_voxels(youth_cuda_handle* h, int stream);
+
 /* ---- parity hooks (blocking) ---- */
 /* volume of sequence `stream`: int16 [dim2][dim1][dim0][2] = (tsdf * 32767, weight) */
 int youth_cuda_debug_read_volume(youth_cuda_handle* h, int stream, int16_t* dst, size_t dst_bytes);

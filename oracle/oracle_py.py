@@ -109,6 +109,7 @@ def lib(fast=False):
             "yo_tsdf_integrate": (None, [CP, C.POINTER(TsdfConfig), C.c_void_p, C.c_void_p, C.c_void_p]),
             "yo_tsdf_raycast": (None, [CP, C.POINTER(TsdfConfig), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
+            "yo_tsdf_surface_voxels": (C.c_int64, [C.POINTER(TsdfConfig), C.c_void_p]),
             "yo_track_sequence_model": (None, [CP, C.POINTER(TsdfConfig), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
         })
     for name, (res, args) in sig.items():
@@ -296,3 +297,7 @@ def track_sequence_model(cfg, tcfg, frames):
     status = np.empty(n, dtype=np.uint32)
     lib().yo_track_sequence_model(C.byref(cfg), C.byref(tcfg), frames.ctypes.data, n, poses.ctypes.data, status.ctypes.data)
     return poses, status
+
+
+def tsdf_surface_voxels(tcfg, vol):
+    return int(lib().yo_tsdf_surface_voxels(C.byref(tcfg), vol.ctypes.data))

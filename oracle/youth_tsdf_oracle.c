@@ -109,6 +109,27 @@ void yo_tsdf_integrate(const yo_config* c, const yo_tsdf_config* t, int16_t* vox
   }
 }
 
+/* Size of the map: observed voxels (weight > 0) whose tsdf changes sign (>= 0 against < 0) towards an observed
+ * +x, +y or +z neighbour -- the voxels the surface passes through.  The dense counterpart of
+ * GetAllMapPoints().size() (reference SLAM.cpp:212-217). */
+int64_t yo_tsdf_surface_voxels(const yo_tsdf_config* t, const int16_t* vox) {
+  const int dx = t->dim[0], dy = t->dim[1], dz = t->dim[2];
+  int64_t n = 0;
+  for (int iz = 0; iz < dz; ++iz)
+    for (int iy = 0; iy < dy; ++iy)
+      for (int ix = 0; ix < dx; ++ix) {
+        const int16_t* v = vox + 2 * (((size_t)iz * dy + iy) * dx + ix);
+        if (v[1] <= 0) continue;
+        const int neg = v[0] < 0;
+        int hit = 0;
+        if (ix + 1 < dx && v[3] > 0 && (v[2] < 0) != neg) hit = 1;
+        if (iy + 1 < dy && v[2 * dx + 1] > 0 && (v[2 * dx] < 0) != neg) hit = 1;
+        if (iz + 1 < dz && v[2 * (size_t)dx * dy + 1] > 0 && (v[2 * (size_t)dx * dy] < 0) != neg) hit = 1;
+        n += hit;
+      }
+  return n;
+}
+
 /* nearest-voxel sample at grid coordinates (voxel centres at integers); YT_UNKNOWN where unobserved */
 static float tsdf_nearest(const yo_tsdf_config* t, const int16_t* vox, float gx, float gy, float gz) {
   int ix = (int)(gx + 0.5f), iy = (int)(gy + 0.5f), iz = (int)(gz + 0.5f);

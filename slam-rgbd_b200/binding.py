@@ -117,6 +117,7 @@ def cuda_lib():
         "youth_tsdf_default_config": (C.c_int, [C.POINTER(TsdfConfig)]),
         "youth_cuda_enable_model": (C.c_int, [H, C.POINTER(TsdfConfig)]),
         "youth_cuda_model_enabled": (C.c_int, [H]),
+        "youth_cuda_model_surface_voxels": (C.c_longlong, [H, C.c_int]),
         "youth_cuda_debug_read_volume": (C.c_int, [H, C.c_int, C.c_void_p, C.c_size_t]),
         "youth_cuda_debug_read_model": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
         "youth_cuda_debug_integrate": (C.c_int, [H, C.c_int, C.c_int, C.c_void_p]),
@@ -352,6 +353,12 @@ class Tracker:
     def enable_model(self, tcfg: TsdfConfig):
         self.tcfg = tcfg
         self._check(self.lib.youth_cuda_enable_model(self.h, C.byref(tcfg)), "youth_cuda_enable_model")
+
+    def surface_voxels(self, stream=0):
+        n = self.lib.youth_cuda_model_surface_voxels(self.h, stream)
+        if n < 0:
+            raise RuntimeError("youth_cuda_model_surface_voxels failed: " + self.lib.youth_cuda_last_error().decode())
+        return int(n)
 
     def read_volume(self, stream=0):
         t = self.tcfg

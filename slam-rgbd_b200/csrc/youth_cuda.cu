@@ -1097,6 +1097,24 @@ static int read_planes(const float2* planes, size_t np, int what, void* dst, siz
   return 1;
 }
 
+extern "C" long long youth_cuda_model_surface_voxels(youth_cuda_handle* h, int stream) {
+  if (!h || !h->m.on || stream < 0 || stream >= h->S) {
+    fail("frame-to-model tracking is not enabled / stream out of range");
+    return -1;
+  }
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return -1;
+  unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(h->sums); /* pair scratch, free between groups */
+  unsigned long long cnt = 0;
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+  if (cudaMemsetAsync(d_cnt, 0, sizeof(cnt), h->stream) != cudaSuccess) return -1;
+  const TsdfGeom& g = h->m.geom;
+  k_tsdf_surface_count<<<1184, 256, 0, h->stream>>>(h->m.vol + (size_t)stream * model_voxels(h), g.dx, g.dy, g.dz, d_cnt);
+  h->launches++;
+  if (cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return -1;
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+  return (long long)cnt;
+}
+
 extern "C" int youth_cuda_debug_read_volume(youth_cuda_handle* h, int stream, int16_t* dst, size_t dst_bytes) {
   if (!h || !dst) return fail("null argument");
   if (!h->m.on) return fail("frame-to-model tracking is not enabled");

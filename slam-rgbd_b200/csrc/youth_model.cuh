@@ -77,6 +77,36 @@ __global__ void __launch_bounds__(256) k_fill_u32(uint32_t* p, size_t n, uint32_
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) p[i] = v;
 }
 
+/* size of the map: observed voxels whose tsdf changes sign towards an observed +x / +y / +z neighbour
+ * (integer count, so the atomic accumulation is order independent) */
+__global__ void __launch_bounds__(256) k_tsdf_surface_count(const short2* __restrict__ vol, int dx, int dy, int dz,
+                                                            unsigned long long* out) {
+  const size_t n = (size_t)dx * dy * dz;
+  unsigned int local = 0;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const short2 v = __ldg(vol + i);
+    if (v.y <= 0) continue;
+    const int ix = (int)(i % dx), iy = (int)((i / dx) % dy), iz = (int)(i / ((size_t)dx * dy));
+    const bool neg = v.x < 0;
+    bool hit = false;
+    if (ix + 1 < dx) {
+      const short2 w = __ldg(vol + i + 1);
+      hit |= w.y > 0 && (w.x < 0) != neg;
+    }
+    if (iy + 1 < dy) {
+      const short2 w = __ldg(vol + i + dx);
+      hit |= w.y > 0 && (w.x < 0) != neg;
+    }
+    if (iz + 1 < dz) {
+      const short2 w = __ldg(vol + i + (size_t)dx * dy);
+      hit |= w.y > 0 && (w.x < 0) != neg;
+    }
+    local += hit ? 1u : 0u;
+  }
+  local = __reduce_add_sync(0xffffffffu, local);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, (unsigned long long)local);
+}
+
 __global__ void __launch_bounds__(256) k_tsdf_integrate(const __grid_constant__ IntegrateParams P) {
   const int zchunks = (P.t.dz + YM_ZCHUNK - 1) / YM_ZCHUNK;
   const int s = P.stream0 + blockIdx.z / zchunks, zc = blockIdx.z % zchunks;

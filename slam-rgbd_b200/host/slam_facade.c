@@ -362,6 +362,15 @@ int isSlamModuleRunning(void) { return atomic_load(&G.running) ? 1 : 0; }
 
 int getSlamMapPoints(void) {
   if (!atomic_load(&G.running) || !G.h) return 0;
+  if (youth_cuda_model_enabled(G.h)) {
+    /* frame-to-model: the map has a size of its own -- the voxels the fused surface passes through
+     * (GetAllMapPoints().size(), SLAM.cpp:212-217) */
+    pthread_mutex_lock(&G.mu);
+    while (G.count > 0 || G.busy > 0) pthread_cond_wait(&G.idle, &G.mu); /* the worker is idle: the handle is ours */
+    const long long n = youth_cuda_model_surface_voxels(G.h, 0);
+    pthread_mutex_unlock(&G.mu);
+    return n < 0 ? 0 : (n > 2147483647LL ? 2147483647 : (int)n);
+  }
   return atomic_load(&G.last_inliers);
 }
 

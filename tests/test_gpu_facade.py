@@ -158,6 +158,7 @@ def test_facade_in_model_mode(pkg, small_seq):
         host.youthSlamDrain()
         poses = np.empty((6, 12), dtype=np.float32)
         assert host.youthSlamGetTrajectory(poses.ctypes.data, None, None, 6) == 6
+        assert host.getSlamMapPoints() > 20000  # the size of the map: surface voxels of the fused volume
         host.stopSlamModule()
     finally:
         del os.environ["YOUTH_SLAM_MODE"]

@@ -141,6 +141,29 @@ def test_model_tracker_drifts_less_than_frame_to_frame(pkg, oracle):
     assert em.max() < 0.02 and em[-1] < ef[-1] * 1.5  # coarse 10 cm voxels at 160x120 already hold the trajectory
 
 
+def test_map_size_counts_surface_voxels(oracle):
+    cfg, t = small_cfgs(oracle, bilateral=0)
+    vol = oracle.tsdf_new(t)
+    assert oracle.tsdf_surface_voxels(t, vol) == 0
+    oracle.tsdf_integrate(cfg, t, vol, np.full((120, 160), 1000.0, dtype=np.float32), IDENT)
+    n = oracle.tsdf_surface_voxels(t, vol)
+    # plane z = 1 m: the sign changes between the voxel layers centred at z = 0.95 and 1.05; count the observed columns
+    layer = vol[21]  # iz = 21 <-> z = 0.95
+    assert (layer[..., 1] > 0).any() and (layer[..., 0][layer[..., 1] > 0] >= 0).all()
+    both = (vol[21][..., 1] > 0) & (vol[22][..., 1] > 0)
+    assert n >= int(both.sum()) > 50
+    # numpy restatement of the definition
+    tsdf, w = vol[..., 0].astype(int), vol[..., 1]
+    hit = np.zeros(w.shape, dtype=bool)
+    for ax in range(3):
+        a = [slice(None)] * 3
+        b = [slice(None)] * 3
+        a[ax], b[ax] = slice(0, -1), slice(1, None)
+        a, b = tuple(a), tuple(b)
+        hit[a] |= (w[a] > 0) & (w[b] > 0) & ((tsdf[a] < 0) != (tsdf[b] < 0))
+    assert n == int(hit.sum())
+
+
 def test_model_symbols_exported(pkg):
     from test_cabi import declared_functions
 
@@ -212,6 +235,8 @@ def test_model_trajectory_bit_exact_small(pkg, oracle):
     trk.reset()
     one = np.stack([trk.track(f) for f in frames])
     assert np.array_equal(one.view(np.uint32), want.view(np.uint32))
+    # the size of the map (observed voxels the surface passes through) equals the statement's count
+    assert trk.surface_voxels() == oracle.tsdf_surface_voxels(otcfg, trk.read_volume()) > 1000
     trk.close()
 
 
