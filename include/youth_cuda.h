@@ -113,6 +113,13 @@ int youth_cuda_track(youth_cuda_handle* h, const uint16_t* depth_mm, uint32_t ti
 int youth_cuda_track_batch(youth_cuda_handle* h, const uint16_t* const* depth, int n_frames,
                            int mem_kind, const uint32_t* timestamps_ms, float* poses_out);
 
+/* Launch schedule of stages 3-5 for groups of more than `pairs_per_group` frame pairs: pairs are
+ * independent, so the whole coarse-to-fine iteration schedule of `pairs_per_group` pairs is run
+ * before the next pairs are touched (their maps stay in L2 from iteration to iteration), groups
+ * alternating over `queues` (1..8) CUDA streams.  pairs_per_group = 0 restores one launch per
+ * iteration over all pairs.  Results do not depend on the schedule. */
+int youth_cuda_set_icp_schedule(youth_cuda_handle* h, int pairs_per_group, int queues);
+
 /* Block until everything enqueued on the handle has finished. */
 int youth_cuda_sync(youth_cuda_handle* h);
 
@@ -148,6 +155,12 @@ int youth_cuda_debug_read(youth_cuda_handle* h, int what, int stream, int frame,
  * int32[h*w]: matched pixel index in the previous frame, or a negative reject code. */
 int youth_cuda_debug_icp(youth_cuda_handle* h, int stream, int frame, int level,
                          const float pose[12], double* sums_out, int32_t* corr_out);
+
+/* Stage 3 divides by v'.z through a reciprocal written out for positive normal floats (no range test,
+ * no slow path).  Returns how many floats with bit patterns in [lo_bits, hi_bits] get a different
+ * result from the correctly rounded reciprocal (must be 0 over the positive normals below 2^126),
+ * -1 on error. */
+long long youth_cuda_debug_rcp_check(youth_cuda_handle* h, uint32_t lo_bits, uint32_t hi_bits);
 
 /* Elapsed device milliseconds between two marks on the handle's stream. */
 int youth_cuda_timer_start(youth_cuda_handle* h);

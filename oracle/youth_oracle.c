@@ -14,6 +14,7 @@
 #define _POSIX_C_SOURCE 200809L
 #include "youth_oracle.h"
 
+#include <float.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -279,7 +280,7 @@ static int icp_pixel(const yo_level* g, float dist2_thr, float cos_thr, const fl
   const float tx = fmaf(P[0], x, fmaf(P[1], y, fmaf(P[2], z, P[3])));
   const float ty = fmaf(P[4], x, fmaf(P[5], y, fmaf(P[6], z, P[7])));
   const float tz = fmaf(P[8], x, fmaf(P[9], y, fmaf(P[10], z, P[11])));
-  if (!(tz > 0.0f)) return YO_REJ_BEHIND;
+  if (!(tz >= FLT_MIN)) return YO_REJ_BEHIND; /* in front of the camera: a positive normal float */
   const float iz = 1.0f / tz;
   const float ur = fmaf(tx * g->fx, iz, g->cx + 0.5f);
   const float vr = fmaf(ty * g->fy, iz, g->cy + 0.5f);

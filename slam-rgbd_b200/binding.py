@@ -96,6 +96,7 @@ def cuda_lib():
         "youth_cuda_destroy": (None, [H]),
         "youth_cuda_track": (C.c_int, [H, C.c_void_p, C.c_uint32, C.c_void_p]),
         "youth_cuda_track_batch": (C.c_int, [H, u16pp, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+        "youth_cuda_set_icp_schedule": (C.c_int, [H, C.c_int, C.c_int]),
         "youth_cuda_sync": (C.c_int, [H]),
         "youth_cuda_reset": (C.c_int, [H, C.c_int]),
         "youth_cuda_frame_count": (C.c_int, [H, C.c_int]),
@@ -106,6 +107,7 @@ def cuda_lib():
         "youth_cuda_host_free": (None, [C.c_void_p]),
         "youth_cuda_debug_read": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
         "youth_cuda_debug_icp": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+        "youth_cuda_debug_rcp_check": (C.c_longlong, [H, C.c_uint32, C.c_uint32]),
         "youth_cuda_timer_start": (C.c_int, [H]),
         "youth_cuda_timer_stop": (C.c_int, [H, C.POINTER(C.c_float)]),
         "youth_cuda_launch_count": (C.c_uint64, [H]),
@@ -280,6 +282,9 @@ class Tracker:
                     "youth_cuda_track")
         return pose
 
+    def set_icp_schedule(self, pairs_per_group, queues=1):
+        self._check(self.lib.youth_cuda_set_icp_schedule(self.h, pairs_per_group, queues), "youth_cuda_set_icp_schedule")
+
     def track_batch_ptrs(self, ptrs, n, mem_kind, ts=None, poses_out=None):
         arr = (C.c_void_p * len(ptrs))(*ptrs)
         self._check(self.lib.youth_cuda_track_batch(
@@ -382,6 +387,11 @@ class Tracker:
         pose = np.ascontiguousarray(pose, dtype=np.float32)
         self._check(self.lib.youth_cuda_debug_raycast(self.h, stream, pose.ctypes.data, hint_frame),
                     "youth_cuda_debug_raycast")
+
+    def debug_rcp_check(self, lo_bits, hi_bits):
+        n = self.lib.youth_cuda_debug_rcp_check(self.h, lo_bits, hi_bits)
+        self._check(n >= 0, "youth_cuda_debug_rcp_check")
+        return n
 
     def timer_start(self):
         self._check(self.lib.youth_cuda_timer_start(self.h), "youth_cuda_timer_start")

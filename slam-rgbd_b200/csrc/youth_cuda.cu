@@ -28,6 +28,7 @@
 #define YK_MAX_CHUNKS 64
 #define YK_GRAPH_MAX_N 8   /* groups of at most this many frames per stream run as one captured CUDA graph */
 #define YK_GRAPH_SLOTS (2 * YK_GRAPH_MAX_N)
+#define YK_ICP_QUEUES 8
 #define YK_ICP_LAST_CTA_MAX_CTAS 444 /* one wave of the 152-register variant: 3 CTAs on each of 148 SMs */
 
 /* ------------------------------------------------------------------ errors */
@@ -63,6 +64,11 @@ struct youth_cuda_handle {
   int max_runs;
   cudaStream_t stream, copy_stream;
   bool own_stream;
+  /* pair-group schedule of stages 3-5 (youth_cuda_set_icp_schedule): all iterations of `icp_group` pairs are
+   * enqueued back to back on one of `icp_nq` side streams, so the maps of a group stay in L2 across iterations */
+  int icp_group, icp_nq;
+  cudaStream_t icp_q[YK_ICP_QUEUES];
+  cudaEvent_t icp_fork, icp_join[YK_ICP_QUEUES];
   /* ring */
   float* depth[YOUTH_MAX_LEVELS];
   float2* maps[YOUTH_MAX_LEVELS]; /* [S][R][3][npix]: (vx,vy) (vz,nx) (ny,nz) planes */
@@ -271,6 +277,14 @@ extern "C" void youth_cuda_destroy(youth_cuda_handle* h) {
   }
   if (h->t0) cudaEventDestroy(h->t0);
   if (h->t1) cudaEventDestroy(h->t1);
+  for (int k = 0; k < YK_ICP_QUEUES; ++k) {
+    if (h->icp_q[k]) {
+      cudaStreamSynchronize(h->icp_q[k]);
+      cudaStreamDestroy(h->icp_q[k]);
+    }
+    if (h->icp_join[k]) cudaEventDestroy(h->icp_join[k]);
+  }
+  if (h->icp_fork) cudaEventDestroy(h->icp_fork);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   free(h->h_count);
@@ -326,6 +340,19 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
     h->own_stream = true;
   }
   CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < YK_ICP_QUEUES; ++k) {
+    CU(cudaStreamCreateWithFlags(&h->icp_q[k], cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->icp_join[k], cudaEventDisableTiming));
+  }
+  CU(cudaEventCreateWithFlags(&h->icp_fork, cudaEventDisableTiming));
+  h->icp_group = 0;
+  h->icp_nq = 1;
+  {
+    const char* g = getenv("YOUTH_ICP_GROUP");
+    const char* q = getenv("YOUTH_ICP_QUEUES");
+    if (g && atoi(g) >= 0) h->icp_group = atoi(g);
+    if (q && atoi(q) >= 1 && atoi(q) <= YK_ICP_QUEUES) h->icp_nq = atoi(q);
+  }
   const size_t slots = (size_t)h->S * h->R;
   for (int l = 0; l < cfg->levels; ++l) {
     CU(dalloc(&h->depth[l], slots * h->npix[l]));
@@ -398,6 +425,15 @@ extern "C" int youth_cuda_init(const youth_cuda_config* cfg, youth_cuda_handle**
   return 1;
 }
 
+extern "C" int youth_cuda_set_icp_schedule(youth_cuda_handle* h, int pairs_per_group, int queues) {
+  if (!h) return fail("null handle");
+  if (pairs_per_group < 0) return fail("pairs_per_group must be >= 0");
+  if (queues < 1 || queues > YK_ICP_QUEUES) return fail("queues must be 1..%d", YK_ICP_QUEUES);
+  h->icp_group = pairs_per_group;
+  h->icp_nq = queues;
+  return 1;
+}
+
 /* ------------------------------------------------------------------ launches */
 
 static RingGeom ring_of(const youth_cuda_handle* h, int n) {
@@ -419,6 +455,15 @@ static void launch_icp(youth_cuda_handle* h, const IcpParams& ip, int pairs, int
     k_icp<false, true><<<grid, 32 * YK_ICP_WARPS, 0, h->stream>>>(ip);
   else
     k_icp<DEBUG, false><<<grid, 32 * YK_ICP_WARPS, 0, h->stream>>>(ip);
+}
+
+/* one iteration of pairs [ip.pair0, ip.pair0 + pairs) on queue q (pair-group schedule; never the debug kernel) */
+static void launch_icp_group(youth_cuda_handle* h, const IcpParams& ip, int pairs, int level, cudaStream_t q, bool last_cta) {
+  const dim3 grid((h->nruns[level] + YK_ICP_WARPS - 1) / YK_ICP_WARPS, pairs);
+  if (last_cta)
+    k_icp<false, true><<<grid, 32 * YK_ICP_WARPS, 0, q>>>(ip);
+  else
+    k_icp<false, false><<<grid, 32 * YK_ICP_WARPS, 0, q>>>(ip);
 }
 
 static IcpParams icp_params(const youth_cuda_handle* h, int level, const RingGeom& ring) {
@@ -522,9 +567,49 @@ static int enqueue_icp(youth_cuda_handle* h, int n) {
   const RingGeom ring = ring_of(h, n);
   const int frames = h->S * n;
   /* stages 3-5: coarse to fine, fixed iteration schedule, one launch per iteration, no host sync */
-  for (int level = c.levels - 1; level >= 0; --level) {
-    const IcpParams ip = icp_params(h, level, ring);
-    for (int it = 0; it < c.iters[level]; ++it) launch_icp<false>(h, ip, frames, level);
+  const int G = h->icp_group;
+  if (G > 0 && frames > G) {
+    /* pair groups: pairs are independent, so the whole coarse-to-fine schedule of G pairs can run before the
+     * next G pairs are touched -- (G + 1) frames of maps stay in L2 for all iterations instead of being
+     * streamed from HBM once per iteration.  Groups go round-robin to side streams so that the tail of one
+     * group's launch (cross-run reduction + solve) overlaps the sweep of another's.  The arithmetic of a
+     * pair does not depend on the grouping (same kernel, same reduction order).  Profiled steps use one
+     * queue so that a launch's CUDA-event duration is that launch alone. */
+    const int ngroups = (frames + G - 1) / G;
+    int K = h->prof_on ? 1 : h->icp_nq;
+    if (K > ngroups) K = ngroups;
+    const bool last_cta = getenv("YOUTH_ICP_GROUP_LAST_CTA") != NULL;
+    if (K > 1) {
+      CU(cudaEventRecord(h->icp_fork, h->stream));
+      for (int k = 0; k < K; ++k) CU(cudaStreamWaitEvent(h->icp_q[k], h->icp_fork, 0));
+    }
+    for (int g = 0; g < ngroups; ++g) {
+      const int pairs = (g + 1) * G <= frames ? G : frames - g * G;
+      for (int level = c.levels - 1; level >= 0; --level) {
+        IcpParams ip = icp_params(h, level, ring);
+        ip.pair0 = g * G;
+        for (int it = 0; it < c.iters[level]; ++it) {
+          if (K > 1) {
+            h->launches++;
+            launch_icp_group(h, ip, pairs, level, h->icp_q[g % K], last_cta);
+          } else {
+            ProfScope ps(h, YOUTH_PROF_ICP0 + level);
+            launch_icp_group(h, ip, pairs, level, h->stream, last_cta);
+          }
+        }
+      }
+      if (h->prof_on && h->prof_n > h->prof_cap - 256 && !prof_flush(h)) return 0;
+    }
+    if (K > 1)
+      for (int k = 0; k < K; ++k) {
+        CU(cudaEventRecord(h->icp_join[k], h->icp_q[k]));
+        CU(cudaStreamWaitEvent(h->stream, h->icp_join[k], 0));
+      }
+  } else {
+    for (int level = c.levels - 1; level >= 0; --level) {
+      const IcpParams ip = icp_params(h, level, ring);
+      for (int it = 0; it < c.iters[level]; ++it) launch_icp<false>(h, ip, frames, level);
+    }
   }
   /* pose chain + trajectory append */
   {
@@ -1196,6 +1281,32 @@ extern "C" int youth_cuda_debug_read(youth_cuda_handle* h, int what, int stream,
     default:
       return fail("unknown debug selector %d", what);
   }
+}
+
+extern "C" long long youth_cuda_debug_rcp_check(youth_cuda_handle* h, uint32_t lo_bits, uint32_t hi_bits) {
+  if (!h) {
+    fail("null handle");
+    return -1;
+  }
+  if (lo_bits > hi_bits) {
+    fail("lo_bits > hi_bits");
+    return -1;
+  }
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return -1;
+  unsigned long long* d = NULL;
+  unsigned long long bad = 0;
+  if (cudaMalloc((void**)&d, sizeof(bad)) != cudaSuccess) return -1;
+  cudaMemsetAsync(d, 0, sizeof(bad), h->stream);
+  k_rcp_check<<<148 * 8, 256, 0, h->stream>>>(lo_bits, hi_bits, d);
+  h->launches++;
+  cudaMemcpyAsync(&bad, d, sizeof(bad), cudaMemcpyDeviceToHost, h->stream);
+  const cudaError_t e = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) {
+    fail("k_rcp_check failed: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  return (long long)bad;
 }
 
 extern "C" int youth_cuda_debug_icp(youth_cuda_handle* h, int stream, int frame, int level, const float pose[12],

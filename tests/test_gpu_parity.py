@@ -263,3 +263,33 @@ def test_independent_handles_from_two_threads(pkg, small_seq):
     assert all(not th.is_alive() for th in ths)
     for k in range(2):
         assert np.array_equal(out[k].view(np.uint32), want.view(np.uint32))
+
+
+def test_reciprocal_is_correctly_rounded_over_all_normals(pkg):
+    """Stage 3's written-out reciprocal (approximation + one Newton step, no range test) against the
+    IEEE reciprocal for EVERY positive normal float below 2^126 -- the only inputs whose quotient the
+    front gate (v'.z >= FLT_MIN; |v'| < 2^21 for finite poses) lets through."""
+    trk = make_tracker(pkg, batch=1, width=64, height=32, levels=1)
+    lo = 0x00800000  # FLT_MIN
+    hi = 0x7E800000 - 1  # just below 2^126
+    assert trk.debug_rcp_check(lo, hi) == 0
+    # the hook itself detects a difference where one exists (denormal inputs take the IEEE slow path)
+    assert trk.debug_rcp_check(0x00000001, 0x000FFFFF) > 0
+    trk.close()
+
+
+def test_icp_schedule_does_not_change_a_bit(pkg, small_seq):
+    """youth_cuda_set_icp_schedule: pair groups on several queues give the trajectory of the plain
+    one-launch-per-iteration schedule, bit for bit (pairs are independent; the reduction order of a
+    pair does not depend on which launch carries it)."""
+    frames, _ = small_seq
+    n = min(len(frames), 12)
+    ref = None
+    for group, queues in [(0, 1), (1, 1), (3, 2), (5, 4), (4, 8)]:
+        trk = make_tracker(pkg, batch=n, traj_capacity=n)
+        trk.set_icp_schedule(group, queues)
+        poses = trk.track_batch([frames[:n]])[0]
+        trk.close()
+        if ref is None:
+            ref = poses
+        assert np.array_equal(poses.view(np.uint32), ref.view(np.uint32)), (group, queues)
