@@ -83,6 +83,7 @@ struct youth_cuda_handle {
   float ws[49];
   float* wr;
   int range_cut;
+  bool ingest_generic; /* YOUTH_INGEST_GENERIC=1: force the per-tap-product bilateral (A/B runs, tests) */
   /* pair state */
   double* pose_d;
   float* pose_f;
@@ -345,6 +346,10 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
     CU(cudaEventCreateWithFlags(&h->icp_join[k], cudaEventDisableTiming));
   }
   CU(cudaEventCreateWithFlags(&h->icp_fork, cudaEventDisableTiming));
+  {
+    const char* g = getenv("YOUTH_INGEST_GENERIC");
+    h->ingest_generic = g && *g == '1';
+  }
   h->icp_group = 0;
   h->icp_nq = 1;
   {
@@ -531,10 +536,14 @@ static int enqueue_preprocess(youth_cuda_handle* h, const uint16_t* const* raw_d
     ip.pyr_thr = 3.0f * c.sigma_range_mm;
     dim3 grid((c.width + YK_TILE_W - 1) / YK_TILE_W, (c.height + YK_TILE_H - 1) / YK_TILE_H, frames);
     ProfScope ps(h, YOUTH_PROF_INGEST);
-    if (c.bilateral)
-      k_ingest<true><<<grid, 256, 0, h->stream>>>(ip);
+    for (int dy = 0; dy < 4; ++dy)
+      for (int dx = 0; dx < 4; ++dx) ip.ws16[dy * 4 + dx] = h->ws[(dy + 3) * 7 + dx + 3];
+    if (!c.bilateral)
+      k_ingest<YK_INGEST_RAW><<<grid, 256, 0, h->stream>>>(ip);
+    else if (h->range_cut + 2 <= YK_WT_STRIDE && !h->ingest_generic)
+      k_ingest<YK_INGEST_BILATERAL_WT><<<grid, 256, 0, h->stream>>>(ip);
     else
-      k_ingest<false><<<grid, 256, 0, h->stream>>>(ip);
+      k_ingest<YK_INGEST_BILATERAL><<<grid, 256, 0, h->stream>>>(ip);
   }
   /* stage 2b */
   {

@@ -293,3 +293,28 @@ def test_icp_schedule_does_not_change_a_bit(pkg, small_seq):
         if ref is None:
             ref = poses
         assert np.array_equal(poses.view(np.uint32), ref.view(np.uint32)), (group, queues)
+
+
+@pytest.mark.parametrize("sigma_range_mm", [30.0, 41.9, 42.5, 60.0])
+def test_bilateral_table_and_generic_paths_match_the_oracle(pkg, oracle, small_seq, sigma_range_mm, monkeypatch):
+    """k_ingest has two bilateral variants: the product table s_wt[class][|diff|] (3 sigma_range + 2 <= 128
+    entries, i.e. up to 42 mm) and the generic per-tap product (any sigma_range).  Both must give the
+    oracle's filtered depth bit for bit; the table variant is also compared with the generic one forced
+    through YOUTH_INGEST_GENERIC=1."""
+    from slam_rgbd_b200 import binding as B
+
+    frames, _ = small_seq
+    out = {}
+    for forced in ("0", "1"):
+        monkeypatch.setenv("YOUTH_INGEST_GENERIC", forced)
+        trk = make_tracker(pkg, batch=2, sigma_range_mm=sigma_range_mm)
+        ocfg = oracle.config_from(trk.cfg)
+        trk.track_batch([frames[:2]])
+        of = oracle.OFrame(ocfg, frames[1])
+        for level in range(trk.cfg.levels):
+            d = trk.debug_read(B.DBG_DEPTH, 1, level)
+            assert np.array_equal(d, of.depth(level)), f"depth level {level} (generic forced: {forced})"
+            out[(forced, level)] = d
+        trk.close()
+    for level in range(3):
+        assert np.array_equal(out[("0", level)], out[("1", level)])
