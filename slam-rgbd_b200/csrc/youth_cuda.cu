@@ -83,6 +83,7 @@ struct youth_cuda_handle {
   float ws[49];
   float* wr;
   int range_cut;
+  int host_range; /* YOUTH_HOST_RANGE: frames per tracking range of host-fed groups (0 = whole group, see host_range_frames) */
   bool ingest_generic; /* YOUTH_INGEST_GENERIC=1: force the per-tap-product bilateral (A/B runs, tests) */
   /* pair state */
   double* pose_d;
@@ -349,15 +350,11 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
   {
     const char* g = getenv("YOUTH_INGEST_GENERIC");
     h->ingest_generic = g && *g == '1';
+    const char* r = getenv("YOUTH_HOST_RANGE");
+    h->host_range = r ? atoi(r) : 0;
   }
   h->icp_group = 0;
   h->icp_nq = 1;
-  {
-    const char* g = getenv("YOUTH_ICP_GROUP");
-    const char* q = getenv("YOUTH_ICP_QUEUES");
-    if (g && atoi(g) >= 0) h->icp_group = atoi(g);
-    if (q && atoi(q) >= 1 && atoi(q) <= YK_ICP_QUEUES) h->icp_nq = atoi(q);
-  }
   const size_t slots = (size_t)h->S * h->R;
   for (int l = 0; l < cfg->levels; ++l) {
     CU(dalloc(&h->depth[l], slots * h->npix[l]));
@@ -450,22 +447,12 @@ static RingGeom ring_of(const youth_cuda_handle* h, int n) {
   return r;
 }
 
-template <bool DEBUG>
-static void launch_icp(youth_cuda_handle* h, const IcpParams& ip, int pairs, int level) {
-  ProfScope ps(h, YOUTH_PROF_ICP0 + level);
+/* one iteration of the pairs ip.f0 .. ip.f0 + ip.fn - 1 of every sequence (`pairs` = S * fn) on stream q.
+ * Few pairs per launch (live / frame-to-model): the latency of the tail matters, share it between the warps
+ * of the last CTA; many pairs: no block barrier, the tails of different pairs overlap anyway. */
+static void launch_icp_on(youth_cuda_handle* h, const IcpParams& ip, int pairs, int level, cudaStream_t q) {
   const dim3 grid((h->nruns[level] + YK_ICP_WARPS - 1) / YK_ICP_WARPS, pairs);
-  /* few pairs per launch (live / frame-to-model): the latency of the tail matters, share it between the
-   * warps of the last CTA; many pairs: no block barrier, the tails of different pairs overlap anyway */
-  if (!DEBUG && (long long)grid.x * pairs <= YK_ICP_LAST_CTA_MAX_CTAS)
-    k_icp<false, true><<<grid, 32 * YK_ICP_WARPS, 0, h->stream>>>(ip);
-  else
-    k_icp<DEBUG, false><<<grid, 32 * YK_ICP_WARPS, 0, h->stream>>>(ip);
-}
-
-/* one iteration of pairs [ip.pair0, ip.pair0 + pairs) on queue q (pair-group schedule; never the debug kernel) */
-static void launch_icp_group(youth_cuda_handle* h, const IcpParams& ip, int pairs, int level, cudaStream_t q, bool last_cta) {
-  const dim3 grid((h->nruns[level] + YK_ICP_WARPS - 1) / YK_ICP_WARPS, pairs);
-  if (last_cta)
+  if ((long long)grid.x * pairs <= YK_ICP_LAST_CTA_MAX_CTAS)
     k_icp<false, true><<<grid, 32 * YK_ICP_WARPS, 0, q>>>(ip);
   else
     k_icp<false, false><<<grid, 32 * YK_ICP_WARPS, 0, q>>>(ip);
@@ -498,6 +485,8 @@ static IcpParams icp_params(const youth_cuda_handle* h, int level, const RingGeo
   ip.min_inliers = h->cfg.min_inliers;
   ip.do_solve = 1;
   ip.model = h->m.on ? h->m.maps[level] : NULL;
+  ip.f0 = 0;
+  ip.fn = ring.n;
   return ip;
 }
 
@@ -570,40 +559,52 @@ static int enqueue_preprocess(youth_cuda_handle* h, const uint16_t* const* raw_d
   return 1;
 }
 
-/* stages 3-5 + pose chain for a whole group of n frames per stream */
-static int enqueue_icp(youth_cuda_handle* h, int n) {
+/* Host-fed groups: frames per tracking range (a multiple of the copy chunk), so that stages 3-5 of the
+ * first range could iterate while later frames are still being copied.  Measured on B200 (300 frames from
+ * pinned host memory, ranges of 160 / 100 frames): no gain -- what the overlap saves (H2D of the later
+ * ranges, 55 GB/s also under load) the shorter launches lose in partial waves and per-launch tails -- so
+ * the default is one range; YOUTH_HOST_RANGE=<frames> keeps the experiment reproducible. */
+static int host_range_frames(const youth_cuda_handle* h, int n_frames, int chunk) {
+  int r = h->host_range;
+  if (r <= 0) return n_frames;
+  r = ((r + chunk - 1) / chunk) * chunk;
+  return r >= n_frames ? n_frames : r;
+}
+
+/* stages 3-5 for frames [f0, f0 + fn) of every stream's group of n frames: coarse to fine, fixed iteration
+ * schedule, one launch per iteration, no host sync.  Pairs are independent, so a group may be tracked in
+ * several frame ranges (host-fed groups: the first range iterates while later frames are still in flight);
+ * the arithmetic of a pair does not depend on which launch carries it. */
+static int enqueue_icp_range(youth_cuda_handle* h, int n, int f0, int fn) {
   const youth_cuda_config& c = h->cfg;
   const RingGeom ring = ring_of(h, n);
-  const int frames = h->S * n;
-  /* stages 3-5: coarse to fine, fixed iteration schedule, one launch per iteration, no host sync */
   const int G = h->icp_group;
-  if (G > 0 && frames > G) {
-    /* pair groups: pairs are independent, so the whole coarse-to-fine schedule of G pairs can run before the
-     * next G pairs are touched -- (G + 1) frames of maps stay in L2 for all iterations instead of being
-     * streamed from HBM once per iteration.  Groups go round-robin to side streams so that the tail of one
-     * group's launch (cross-run reduction + solve) overlaps the sweep of another's.  The arithmetic of a
-     * pair does not depend on the grouping (same kernel, same reduction order).  Profiled steps use one
-     * queue so that a launch's CUDA-event duration is that launch alone. */
-    const int ngroups = (frames + G - 1) / G;
+  if (G > 0 && fn > G) {
+    /* frame-range schedule (youth_cuda_set_icp_schedule): the whole coarse-to-fine schedule of G frames per
+     * sequence before the next G are touched, ranges round-robin over side streams so that the tail of one
+     * range's launch (cross-run reduction + solve) overlaps the sweep of another's.  Measured on B200: no
+     * gain over one launch per iteration (profiles/README.md); kept as a tested knob.  Profiled steps use
+     * one queue so that a launch's CUDA-event duration is that launch alone. */
+    const int ngroups = (fn + G - 1) / G;
     int K = h->prof_on ? 1 : h->icp_nq;
     if (K > ngroups) K = ngroups;
-    const bool last_cta = getenv("YOUTH_ICP_GROUP_LAST_CTA") != NULL;
     if (K > 1) {
       CU(cudaEventRecord(h->icp_fork, h->stream));
       for (int k = 0; k < K; ++k) CU(cudaStreamWaitEvent(h->icp_q[k], h->icp_fork, 0));
     }
     for (int g = 0; g < ngroups; ++g) {
-      const int pairs = (g + 1) * G <= frames ? G : frames - g * G;
+      const int gn = (g + 1) * G <= fn ? G : fn - g * G;
       for (int level = c.levels - 1; level >= 0; --level) {
         IcpParams ip = icp_params(h, level, ring);
-        ip.pair0 = g * G;
+        ip.f0 = f0 + g * G;
+        ip.fn = gn;
         for (int it = 0; it < c.iters[level]; ++it) {
           if (K > 1) {
             h->launches++;
-            launch_icp_group(h, ip, pairs, level, h->icp_q[g % K], last_cta);
+            launch_icp_on(h, ip, h->S * gn, level, h->icp_q[g % K]);
           } else {
             ProfScope ps(h, YOUTH_PROF_ICP0 + level);
-            launch_icp_group(h, ip, pairs, level, h->stream, last_cta);
+            launch_icp_on(h, ip, h->S * gn, level, h->stream);
           }
         }
       }
@@ -616,34 +617,48 @@ static int enqueue_icp(youth_cuda_handle* h, int n) {
       }
   } else {
     for (int level = c.levels - 1; level >= 0; --level) {
-      const IcpParams ip = icp_params(h, level, ring);
-      for (int it = 0; it < c.iters[level]; ++it) launch_icp<false>(h, ip, frames, level);
+      IcpParams ip = icp_params(h, level, ring);
+      ip.f0 = f0;
+      ip.fn = fn;
+      for (int it = 0; it < c.iters[level]; ++it) {
+        ProfScope ps(h, YOUTH_PROF_ICP0 + level);
+        launch_icp_on(h, ip, h->S * fn, level, h->stream);
+      }
     }
-  }
-  /* pose chain + trajectory append */
-  {
-    ComposeParams cp;
-    memset(&cp, 0, sizeof(cp));
-    cp.ring = ring;
-    cp.seq_count = h->seq_count;
-    cp.world = h->world;
-    cp.pose_d = h->pose_d;
-    cp.sums = h->sums;
-    cp.pair_status = h->pair_status;
-    cp.traj = h->traj;
-    cp.traj_status = h->traj_status;
-    cp.last_inliers = h->last_inliers;
-    cp.head = h->d_head;
-    cp.cap = c.traj_capacity;
-    cp.world_f = h->m.on ? h->m.world_f : NULL;
-    cp.last_status = h->m.on ? h->m.last_status : NULL;
-    ProfScope ps(h, YOUTH_PROF_MISC);
-    k_compose<<<h->S, 128, 0, h->stream>>>(cp);
   }
   CU(cudaGetLastError());
   if (h->prof_on && h->prof_n > h->prof_cap - 256) return prof_flush(h);
   return 1;
 }
+
+/* pose chain + trajectory append for the whole group (after every range of stages 3-5) */
+static int enqueue_compose(youth_cuda_handle* h, int n) {
+  const RingGeom ring = ring_of(h, n);
+  ComposeParams cp;
+  memset(&cp, 0, sizeof(cp));
+  cp.ring = ring;
+  cp.seq_count = h->seq_count;
+  cp.world = h->world;
+  cp.pose_d = h->pose_d;
+  cp.sums = h->sums;
+  cp.pair_status = h->pair_status;
+  cp.traj = h->traj;
+  cp.traj_status = h->traj_status;
+  cp.last_inliers = h->last_inliers;
+  cp.head = h->d_head;
+  cp.cap = h->cfg.traj_capacity;
+  cp.world_f = h->m.on ? h->m.world_f : NULL;
+  cp.last_status = h->m.on ? h->m.last_status : NULL;
+  {
+    ProfScope ps(h, YOUTH_PROF_MISC);
+    k_compose<<<h->S, 128, 0, h->stream>>>(cp);
+  }
+  CU(cudaGetLastError());
+  return 1;
+}
+
+/* stages 3-5 + pose chain for a whole group of n frames per stream */
+static int enqueue_icp(youth_cuda_handle* h, int n) { return enqueue_icp_range(h, n, 0, n) && enqueue_compose(h, n); }
 
 /* ------------------------------------------------------------------ frame-to-model (include/youth_model.h) */
 
@@ -918,11 +933,13 @@ extern "C" int youth_cuda_track_batch(youth_cuda_handle* h, const uint16_t* cons
       CU(cudaGraphLaunch(h->graphs[gi].exec, h->stream));
       h->launches += h->graphs[gi].launches;
     } else {
-      /* copy and preprocess in chunks: the H2D of chunk c+1 overlaps ingest of chunk c */
+      /* copy and preprocess in chunks: the H2D of chunk c+1 overlaps ingest of chunk c; and track in
+       * frame ranges: stages 3-5 of range r iterate while the copy stream brings in range r+1 */
       int ch = (n_frames + YK_MAX_CHUNKS - 1) / YK_MAX_CHUNKS;
       if (ch < YK_CHUNK_FRAMES) ch = YK_CHUNK_FRAMES;
+      const int range = host_range_frames(h, n_frames, ch);
       for (int s = 0; s < h->S; ++s) dev_ptrs[s] = h->raw[k] + (size_t)s * n_frames * frame_px;
-      int ci = 0;
+      int ci = 0, tracked = 0;
       for (int f0 = 0; f0 < n_frames; f0 += ch, ++ci) {
         const int cn = n_frames - f0 < ch ? n_frames - f0 : ch;
         const size_t off = (size_t)f0 * frame_px, bytes = (size_t)cn * frame_px * sizeof(uint16_t);
@@ -939,8 +956,14 @@ extern "C" int youth_cuda_track_batch(youth_cuda_handle* h, const uint16_t* cons
         CU(cudaEventRecord(h->chunk_ready[k][ci], h->copy_stream));
         CU(cudaStreamWaitEvent(h->stream, h->chunk_ready[k][ci], 0));
         if (!enqueue_preprocess(h, dev_ptrs, n_frames, f0, cn)) return 0;
+        const int have = f0 + cn;
+        if (have - tracked >= range && n_frames - have >= range / 2) { /* no short last range */
+          if (!enqueue_icp_range(h, n_frames, tracked, have - tracked)) return 0;
+          tracked = have;
+        }
       }
-      if (!enqueue_icp(h, n_frames)) return 0;
+      if (tracked < n_frames && !enqueue_icp_range(h, n_frames, tracked, n_frames - tracked)) return 0;
+      if (!enqueue_compose(h, n_frames)) return 0;
     }
     CU(cudaEventRecord(h->raw_free[k], h->stream));
     h->raw_used[k] = true;
@@ -1027,7 +1050,8 @@ extern "C" int youth_cuda_track_batch_packed(youth_cuda_handle* h, const uint8_t
   for (int s = 0; s < h->S; ++s) dev_ptrs[s] = h->raw[k] + (size_t)s * n_frames * frame_px;
   int ch = (n_frames + YK_MAX_CHUNKS - 1) / YK_MAX_CHUNKS;
   if (ch < YK_CHUNK_FRAMES) ch = YK_CHUNK_FRAMES;
-  int ci = 0;
+  const int range = host_range_frames(h, n_frames, ch);
+  int ci = 0, tracked = 0;
   for (int f0 = 0; f0 < n_frames; f0 += ch, ++ci) {
     const int cn = n_frames - f0 < ch ? n_frames - f0 : ch;
     for (int s = 0; s < h->S; ++s) {
@@ -1046,11 +1070,17 @@ extern "C" int youth_cuda_track_batch_packed(youth_cuda_handle* h, const uint8_t
         return 0;
     }
     if (!enqueue_preprocess(h, dev_ptrs, n_frames, f0, cn)) return 0;
+    const int have = f0 + cn;
+    if (have - tracked >= range && n_frames - have >= range / 2) {
+      if (!enqueue_icp_range(h, n_frames, tracked, have - tracked)) return 0;
+      tracked = have;
+    }
   }
   CU(cudaMemcpyAsync(c->h_err, c->d_err, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaEventRecord(h->pk_free, h->stream));
   h->pk_used = true;
-  if (!enqueue_icp(h, n_frames)) return 0;
+  if (tracked < n_frames && !enqueue_icp_range(h, n_frames, tracked, n_frames - tracked)) return 0;
+  if (!enqueue_compose(h, n_frames)) return 0;
   CU(cudaEventRecord(h->raw_free[k], h->stream));
   h->raw_used[k] = true;
   if (!finish_group(h, n_frames, timestamps_ms, poses_out)) return 0;
@@ -1336,7 +1366,11 @@ extern "C" int youth_cuda_debug_icp(youth_cuda_handle* h, int stream, int frame,
   ip.dbg_stream = stream;
   ip.do_solve = 0;
   ip.model = NULL; /* always frame `frame` against frame - 1, also on a frame-to-model handle */
-  launch_icp<true>(h, ip, 1, level);
+  {
+    ProfScope ps(h, YOUTH_PROF_ICP0 + level);
+    const dim3 grid((h->nruns[level] + YK_ICP_WARPS - 1) / YK_ICP_WARPS, 1);
+    k_icp<true, false><<<grid, 32 * YK_ICP_WARPS, 0, h->stream>>>(ip);
+  }
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(sums_out, h->sums, sizeof(double) * 32, cudaMemcpyDeviceToHost, h->stream));
   if (corr_out)
