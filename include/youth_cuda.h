@@ -134,6 +134,16 @@ int youth_cuda_frame_count(youth_cuda_handle* h, int stream);
 int youth_cuda_get_trajectory(youth_cuda_handle* h, int stream, int first, int max_frames,
                               float* poses_out, uint32_t* timestamps_out, uint32_t* status_out);
 
+/* Stream-ordered variant: enqueues the copies behind everything submitted so far and returns the number of
+ * frames that will be copied (-1 on error) without waiting; *ticket_out names their completion.
+ * poses_out / status_out should be page-locked (youth_cuda_host_alloc) for the copy to be asynchronous.
+ * youth_cuda_wait_ticket blocks until that read-back has landed (tickets complete in order).  Keeping
+ * two groups in flight -- submit g+1, then wait for g -- hides the host-to-device copy of g+1 under the
+ * kernels of g. */
+int youth_cuda_read_trajectory_async(youth_cuda_handle* h, int stream, int first, int max_frames,
+                                     float* poses_out, uint32_t* status_out, uint64_t* ticket_out);
+int youth_cuda_wait_ticket(youth_cuda_handle* h, uint64_t ticket);
+
 /* Inlier correspondences of the last tracked frame of `stream` at the finest level
  * (last iteration); blocking. */
 int youth_cuda_last_inliers(youth_cuda_handle* h, int stream);

@@ -101,6 +101,8 @@ def cuda_lib():
         "youth_cuda_reset": (C.c_int, [H, C.c_int]),
         "youth_cuda_frame_count": (C.c_int, [H, C.c_int]),
         "youth_cuda_get_trajectory": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+        "youth_cuda_read_trajectory_async": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
+        "youth_cuda_wait_ticket": (C.c_int, [H, C.c_uint64]),
         "youth_cuda_last_inliers": (C.c_int, [H, C.c_int]),
         "youth_cuda_trajectory_device_ptr": (C.c_void_p, [H, C.c_int]),
         "youth_cuda_host_alloc": (C.c_void_p, [C.c_size_t]),
@@ -329,6 +331,16 @@ class Tracker:
         if got < 0:
             raise RuntimeError("youth_cuda_get_trajectory failed: " + self.lib.youth_cuda_last_error().decode())
         return poses[:got], ts[:got], st[:got]
+
+    def read_trajectory_async(self, poses_ptr, n, stream=0, first=0, status_ptr=None):
+        """Stream-ordered read-back into (pinned) host memory; returns (frames, ticket)."""
+        t = C.c_uint64()
+        got = self.lib.youth_cuda_read_trajectory_async(self.h, stream, first, n, poses_ptr, status_ptr, C.byref(t))
+        self._check(got >= 0, "youth_cuda_read_trajectory_async")
+        return got, t.value
+
+    def wait_ticket(self, ticket):
+        self._check(self.lib.youth_cuda_wait_ticket(self.h, ticket), "youth_cuda_wait_ticket")
 
     def last_inliers(self, stream=0):
         return self.lib.youth_cuda_last_inliers(self.h, stream)

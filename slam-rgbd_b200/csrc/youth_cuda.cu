@@ -29,6 +29,7 @@
 #define YK_GRAPH_MAX_N 8   /* groups of at most this many frames per stream run as one captured CUDA graph */
 #define YK_GRAPH_SLOTS (2 * YK_GRAPH_MAX_N)
 #define YK_ICP_QUEUES 8
+#define YK_TICKETS 16
 #define YK_ICP_LAST_CTA_MAX_CTAS 444 /* one wave of the 152-register variant: 3 CTAs on each of 148 SMs */
 
 /* ------------------------------------------------------------------ errors */
@@ -83,6 +84,8 @@ struct youth_cuda_handle {
   float ws[49];
   float* wr;
   int range_cut;
+  cudaEvent_t ticket_ev[YK_TICKETS]; /* youth_cuda_read_trajectory_async / youth_cuda_wait_ticket */
+  uint64_t ticket_next;
   int host_range; /* YOUTH_HOST_RANGE: frames per tracking range of host-fed groups (0 = whole group, see host_range_frames) */
   bool ingest_generic; /* YOUTH_INGEST_GENERIC=1: force the per-tap-product bilateral (A/B runs, tests) */
   /* pair state */
@@ -287,6 +290,8 @@ extern "C" void youth_cuda_destroy(youth_cuda_handle* h) {
     if (h->icp_join[k]) cudaEventDestroy(h->icp_join[k]);
   }
   if (h->icp_fork) cudaEventDestroy(h->icp_fork);
+  for (int k = 0; k < YK_TICKETS; ++k)
+    if (h->ticket_ev[k]) cudaEventDestroy(h->ticket_ev[k]);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   free(h->h_count);
@@ -1155,6 +1160,47 @@ extern "C" int youth_cuda_get_trajectory(youth_cuda_handle* h, int stream, int f
   }
   if (timestamps_out) memcpy(timestamps_out, h->h_ts + base, sizeof(uint32_t) * n);
   return n;
+}
+
+/* Stream-ordered read-back: the copies are enqueued behind everything submitted so far and the call
+ * returns; the ticket names an event recorded behind them.  With it a caller keeps two groups in flight
+ * -- submit group g+1 (its H2D runs on the copy stream under group g's kernels), then collect group g. */
+extern "C" int youth_cuda_read_trajectory_async(youth_cuda_handle* h, int stream, int first, int max_frames,
+                                                float* poses_out, uint32_t* status_out, uint64_t* ticket_out) {
+  if (!h || stream < 0 || stream >= h->S || first < 0 || max_frames < 0 || !ticket_out) {
+    fail("bad argument");
+    return -1;
+  }
+  int n = h->h_count[stream] - first;
+  if (n > max_frames) n = max_frames;
+  if (n < 0) n = 0;
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return -1;
+  const size_t base = (size_t)stream * h->cfg.traj_capacity + first;
+  cudaError_t e = cudaSuccess;
+  if (n > 0 && poses_out)
+    e = cudaMemcpyAsync(poses_out, h->traj + base * 12, sizeof(float) * 12 * n, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && n > 0 && status_out)
+    e = cudaMemcpyAsync(status_out, h->traj_status + base, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, h->stream);
+  const uint64_t t = h->ticket_next;
+  cudaEvent_t& ev = h->ticket_ev[t % YK_TICKETS];
+  if (e == cudaSuccess && !ev) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventRecord(ev, h->stream);
+  if (e != cudaSuccess) {
+    fail("asynchronous trajectory read-back failed: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  h->ticket_next = t + 1;
+  *ticket_out = t;
+  return n;
+}
+
+extern "C" int youth_cuda_wait_ticket(youth_cuda_handle* h, uint64_t ticket) {
+  if (!h) return fail("null handle");
+  if (ticket >= h->ticket_next) return fail("unknown ticket");
+  if (ticket + YK_TICKETS < h->ticket_next) return 1; /* its event was re-used by a later read on the same stream: long done or covered */
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaEventSynchronize(h->ticket_ev[ticket % YK_TICKETS]));
+  return 1;
 }
 
 extern "C" int youth_cuda_last_inliers(youth_cuda_handle* h, int stream) {

@@ -318,3 +318,43 @@ def test_bilateral_table_and_generic_paths_match_the_oracle(pkg, oracle, small_s
         trk.close()
     for level in range(3):
         assert np.array_equal(out[("0", level)], out[("1", level)])
+
+
+def test_two_groups_in_flight_give_the_blocking_results(pkg, small_seq):
+    """youth_cuda_read_trajectory_async / youth_cuda_wait_ticket: submit group g+1 before collecting group g
+    (host-fed, pinned); every collected trajectory equals the blocking call's, bit for bit, and tickets
+    complete in order."""
+    import ctypes as C
+
+    from slam_rgbd_b200 import binding as B
+
+    frames, _ = small_seq
+    n = len(frames)
+    trk = make_tracker(pkg, batch=n, traj_capacity=n)
+    ref = trk.track_batch([frames])[0].copy()
+    pin = trk.lib.youth_cuda_host_alloc(frames.nbytes)
+    C.memmove(pin, frames.ctypes.data, frames.nbytes)
+    res = [trk.lib.youth_cuda_host_alloc(n * 48) for _ in range(2)]
+    views = [np.ctypeslib.as_array((C.c_float * (n * 12)).from_address(p)).reshape(n, 12) for p in res]
+    pending, seen = [], []
+    for i in range(5):
+        trk.reset()
+        trk.track_batch_ptrs([pin], n, B.MEM_HOST_PINNED)
+        views[i % 2][...] = -1.0  # step i-2 has been collected: poison the buffer so that the read-back must land
+        got, ticket = trk.read_trajectory_async(res[i % 2], n)
+        assert got == n
+        pending.append((i, ticket))
+        if len(pending) > 1:
+            j, t = pending.pop(0)
+            trk.wait_ticket(t)
+            seen.append(t)
+            assert np.array_equal(views[j % 2].view(np.uint32), ref.view(np.uint32)), f"step {j}"
+    j, t = pending.pop(0)
+    trk.wait_ticket(t)
+    seen.append(t)
+    assert np.array_equal(views[j % 2].view(np.uint32), ref.view(np.uint32))
+    assert seen == sorted(seen)
+    trk.wait_ticket(seen[0])  # waiting again on a finished ticket returns at once
+    for p in res + [pin]:
+        trk.lib.youth_cuda_host_free(p)
+    trk.close()
