@@ -592,6 +592,43 @@ def run_ours(args):
         streaming = {"frames_per_sec": nlive / dt, "us_per_frame": dt / nlive * 1e6,
                      "what": "youth_cuda_track: one pageable host frame in, blocking pose out, batch 1"}
 
+    # ---- the reference-facing facade (include/SLAM.h): one processSlamFrame() call per frame from a producer
+    # thread (synchronous copy into the pinned host ring, SLAM.cpp:133-134), worker thread with two runs of
+    # 64 frames in flight, youthSlamDrain + trajectory read-back at the end of every pass
+    facade = None
+    if (Wd, Hd, S) == (W, H, 1) and args.mode != "model" and args.levels == 3 and not args.ppt:
+        try:
+            os.environ["YOUTH_SLAM_DEVICE"] = str(local)
+            os.environ["YOUTH_SLAM_TRAJ_CAPACITY"] = str(FRAMES)
+            host = pkg.host_lib()
+            host.youthSlamSetOptions(1, 64)  # lossless, 64 frames per launch group (the facade's maximum)
+            host.initSlamModule(None, None)
+            if host.isSlamModuleRunning() == 1:
+                fposes = np.empty((FRAMES, 12), dtype=np.float32)
+                ptrs = [frames[0][i].ctypes.data for i in range(FRAMES)]
+
+                def facade_pass():
+                    host.resetSlam()
+                    for i in range(FRAMES):
+                        assert host.processSlamFrame(ptrs[i], None, W, H, 33 * i) == 1
+                    host.youthSlamDrain()
+                    assert host.youthSlamGetTrajectory(fposes.ctypes.data, None, None, FRAMES) == FRAMES
+
+                for _ in range(2):
+                    facade_pass()
+                fsteps = max(1, min(args.steps, 10))
+                t0 = time.perf_counter()
+                for _ in range(fsteps):
+                    facade_pass()
+                fdt = time.perf_counter() - t0
+                facade = {"frames_per_sec": FRAMES * fsteps / fdt, "steps": fsteps,
+                          "bit_identical_to_device_arm": bool(np.array_equal(fposes.view(np.uint32), poses.view(np.uint32))),
+                          "what": "SLAM.h facade: processSlamFrame() per frame (pageable host frame copied into the pinned "
+                                  "ring by the caller's thread), lossless, 64 frames per launch group, two groups in flight"}
+                host.stopSlamModule()
+        except Exception as e:  # the facade arm is informative only
+            facade = {"error": str(e)}
+
     threads = max(1, min(host_threads(), 32))
     fpt = max(3, int(61 * (W * H) / (Wd * Hd)))  # 60 frame pairs per thread at 640x480: about 10-15 s of CPU work
     if args.mode == "model":  # the frame-to-model statement (fusion + ray cast on top of the same ICP), parity build
@@ -636,6 +673,7 @@ def run_ours(args):
                                        "frames_flagged_lost": lost},
         "frames_per_sec_per_gpu": value / world,
         "streaming_single_frame": streaming,
+        "facade": facade,
         "packed_input": packed_info,
     }
     emit(line)

@@ -143,6 +143,9 @@ int youth_cuda_get_trajectory(youth_cuda_handle* h, int stream, int first, int m
 int youth_cuda_read_trajectory_async(youth_cuda_handle* h, int stream, int first, int max_frames,
                                      float* poses_out, uint32_t* status_out, uint64_t* ticket_out);
 int youth_cuda_wait_ticket(youth_cuda_handle* h, uint64_t ticket);
+/* Stream-ordered youth_cuda_last_inliers: covered by the ticket of a youth_cuda_read_trajectory_async
+ * issued after it. */
+int youth_cuda_read_last_inliers_async(youth_cuda_handle* h, int stream, int* inliers_out);
 
 /* Inlier correspondences of the last tracked frame of `stream` at the finest level
  * (last iteration); blocking. */

@@ -103,6 +103,7 @@ def cuda_lib():
         "youth_cuda_get_trajectory": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
         "youth_cuda_read_trajectory_async": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
         "youth_cuda_wait_ticket": (C.c_int, [H, C.c_uint64]),
+        "youth_cuda_read_last_inliers_async": (C.c_int, [H, C.c_int, C.c_void_p]),
         "youth_cuda_last_inliers": (C.c_int, [H, C.c_int]),
         "youth_cuda_trajectory_device_ptr": (C.c_void_p, [H, C.c_int]),
         "youth_cuda_host_alloc": (C.c_void_p, [C.c_size_t]),

@@ -1194,6 +1194,13 @@ extern "C" int youth_cuda_read_trajectory_async(youth_cuda_handle* h, int stream
   return n;
 }
 
+extern "C" int youth_cuda_read_last_inliers_async(youth_cuda_handle* h, int stream, int* inliers_out) {
+  if (!h || stream < 0 || stream >= h->S || !inliers_out) return fail("bad argument");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaMemcpyAsync(inliers_out, h->last_inliers + stream, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  return 1;
+}
+
 extern "C" int youth_cuda_wait_ticket(youth_cuda_handle* h, uint64_t ticket) {
   if (!h) return fail("null handle");
   if (ticket >= h->ticket_next) return fail("unknown ticket");

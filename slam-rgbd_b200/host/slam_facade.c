@@ -7,7 +7,8 @@
  *     (ownership rule of SLAM.cpp:133-134: the caller may reuse its buffer on return);
  *   - a worker thread that hands runs of consecutive ring slots to
  *     youth_cuda_track_batch(), i.e. the device-resident frame ring is fed straight
- *     from the host ring with one async H2D per run;
+ *     from the host ring with one async H2D per run, two runs in flight (the copy of a
+ *     run overlaps the kernels of the run before);
  *   - the reference's lossy back-pressure (more than 10 queued -> drop oldest down to 5,
  *     SLAM.cpp:163-167) as the default, and a lossless mode (producer blocks) for
  *     replay / benchmarking, where dropping frames would make parity meaningless.
@@ -56,13 +57,62 @@ static struct {
 
 static size_t frame_px(void) { return (size_t)G.cfg.width * (size_t)G.cfg.height; }
 
+/* A run of ring slots handed to the tracker and not collected yet.  The worker keeps up to two in
+ * flight: it submits run g+1 (asynchronous youth_cuda_track_batch: its H2D copy runs on the copy stream
+ * under the kernels of run g) before it waits for run g, publishes its poses and releases its slots.
+ * With an empty queue it collects at once, so a lone live frame is not delayed. */
+typedef struct {
+  int valid, ok, n, first, base, buf;
+  uint64_t ticket;
+} PendingRun;
+
+static void collect_run(const PendingRun* r, float* const poses[2], int* const inl[2]) {
+  long sent = 0;
+  int ok = r->ok;
+  if (ok && !youth_cuda_wait_ticket(G.h, r->ticket)) {
+    fprintf(stderr, "AlgorithmModule: tracking failed: %s\n", youth_cuda_last_error());
+    ok = 0;
+  }
+  if (ok) {
+    atomic_store(&G.last_inliers, *inl[r->buf]);
+    if (G.pose_mq != (mqd_t)-1) {
+      /* pose egress (SURVEY.md section 8(f) row 2): one MSG_TYPE_POSE message per tracked frame on the
+       * logger->viewer queue; non-blocking, a full queue drops the pose rather than stalling tracking */
+      const uint32_t in = (uint32_t)*inl[r->buf];
+      char msg[sizeof(MessageHeader) + sizeof(YouthPoseMsg)];
+      for (int i = 0; i < r->n; ++i) {
+        const size_t len = youth_pose_msg_build(msg, r->base + i, G.ts[r->first + i], poses[r->buf] + 12 * (size_t)i, 0u, in);
+        if (mq_send(G.pose_mq, msg, len, 0) == 0) ++sent;
+      }
+    }
+  }
+  pthread_mutex_lock(&G.mu);
+  G.busy -= r->n;
+  G.poses_sent += sent;
+  G.tracked += ok ? r->n : 0;
+  pthread_cond_broadcast(&G.nonfull);
+  if (G.count == 0 && G.busy == 0) pthread_cond_broadcast(&G.idle);
+  pthread_mutex_unlock(&G.mu);
+}
+
 static void* worker_main(void* arg) {
   (void)arg;
-  float* poses = (float*)malloc(sizeof(float) * 12 * (size_t)G.batch);
-  pthread_mutex_lock(&G.mu);
+  float* poses[2];
+  int* inl[2];
+  for (int k = 0; k < 2; ++k) {
+    poses[k] = (float*)youth_cuda_host_alloc(sizeof(float) * 12 * (size_t)G.batch);
+    inl[k] = (int*)youth_cuda_host_alloc(sizeof(int));
+  }
+  PendingRun pend;
+  memset(&pend, 0, sizeof(pend));
+  int turn = 0;
   for (;;) {
-    while (G.count == 0 && !atomic_load(&G.stop_req)) pthread_cond_wait(&G.nonempty, &G.mu);
-    if (G.count == 0 && atomic_load(&G.stop_req)) break;
+    pthread_mutex_lock(&G.mu);
+    while (G.count == 0 && !pend.valid && !atomic_load(&G.stop_req)) pthread_cond_wait(&G.nonempty, &G.mu);
+    if (G.count == 0 && !pend.valid) { /* stop requested and everything collected */
+      pthread_mutex_unlock(&G.mu);
+      break;
+    }
     /* claim the longest run of consecutive slots: contiguous in the pinned ring, at most
      * one batch.  Claimed frames leave the queue at once; `busy` fences their slots. */
     int n = G.count;
@@ -71,35 +121,33 @@ static void* worker_main(void* arg) {
     const int first = G.head;
     G.head = (G.head + n) % G.qcap;
     G.count -= n;
-    G.busy = n;
+    G.busy += n;
     pthread_mutex_unlock(&G.mu);
 
-    const uint16_t* src[1] = {G.ring + frame_px() * (size_t)first};
-    const int ok = youth_cuda_track_batch(G.h, src, n, YOUTH_MEM_HOST_PINNED, G.ts + first, poses);
-    if (!ok) fprintf(stderr, "AlgorithmModule: tracking failed: %s\n", youth_cuda_last_error());
-    else atomic_store(&G.last_inliers, youth_cuda_last_inliers(G.h, 0));
-
-    long sent = 0;
-    if (ok && G.pose_mq != (mqd_t)-1) {
-      /* pose egress (SURVEY.md section 8(f) row 2): one MSG_TYPE_POSE message per tracked frame on the
-       * logger->viewer queue; non-blocking, a full queue drops the pose rather than stalling tracking */
-      const int base = youth_cuda_frame_count(G.h, 0) - n;
-      const uint32_t inl = (uint32_t)atomic_load(&G.last_inliers);
-      char msg[sizeof(MessageHeader) + sizeof(YouthPoseMsg)];
-      for (int i = 0; i < n; ++i) {
-        const size_t len = youth_pose_msg_build(msg, base + i, G.ts[first + i], poses + 12 * (size_t)i, 0u, inl);
-        if (mq_send(G.pose_mq, msg, len, 0) == 0) ++sent;
+    PendingRun cur;
+    memset(&cur, 0, sizeof(cur));
+    if (n > 0) {
+      const uint16_t* src[1] = {G.ring + frame_px() * (size_t)first};
+      cur.valid = 1;
+      cur.n = n;
+      cur.first = first;
+      cur.buf = turn;
+      turn ^= 1;
+      cur.ok = youth_cuda_track_batch(G.h, src, n, YOUTH_MEM_HOST_PINNED, G.ts + first, NULL);
+      cur.base = youth_cuda_frame_count(G.h, 0) - n;
+      if (cur.ok) {
+        cur.ok = youth_cuda_read_last_inliers_async(G.h, 0, inl[cur.buf]) &&
+                 youth_cuda_read_trajectory_async(G.h, 0, cur.base, n, poses[cur.buf], NULL, &cur.ticket) == n;
       }
+      if (!cur.ok) fprintf(stderr, "AlgorithmModule: tracking failed: %s\n", youth_cuda_last_error());
     }
-    pthread_mutex_lock(&G.mu);
-    G.busy = 0;
-    G.poses_sent += sent;
-    G.tracked += ok ? n : 0;
-    pthread_cond_broadcast(&G.nonfull);
-    if (G.count == 0) pthread_cond_broadcast(&G.idle);
+    if (pend.valid) collect_run(&pend, poses, inl);
+    pend = cur;
   }
-  pthread_mutex_unlock(&G.mu);
-  free(poses);
+  for (int k = 0; k < 2; ++k) {
+    youth_cuda_host_free(poses[k]);
+    youth_cuda_host_free(inl[k]);
+  }
   return NULL;
 }
 
@@ -149,7 +197,7 @@ void initSlamModule(const char* config_file, const char* vocabulary_file) {
       }
     }
   }
-  G.qcap = QUEUE_HIGH_WATER + 2 + 2 * G.batch; /* queue + one claimed run always fit */
+  G.qcap = QUEUE_HIGH_WATER + 2 + 3 * G.batch; /* queue + the two runs in flight always fit */
   G.ring = (uint16_t*)youth_cuda_host_alloc(frame_px() * sizeof(uint16_t) * (size_t)G.qcap);
   G.ts = (uint32_t*)calloc((size_t)G.qcap, sizeof(uint32_t));
   if (!G.ring || !G.ts) {

@@ -245,15 +245,20 @@ def test_independent_handles_from_two_threads(pkg, small_seq):
     alone.close()
     out = [None, None]
 
+    errors = [None, None]
+
     def work(k):
-        t = B.Tracker(pkg.default_config(batch=3 if k else 2))
-        n = 3 if k else 2
-        res = []
-        for rep in range(4):
-            t.reset()
-            res = [t.track_batch([frames[a:a + n]])[0] for a in range(0, 6, n)]
-        out[k] = np.concatenate(res)
-        t.close()
+        try:
+            t = B.Tracker(pkg.default_config(batch=3 if k else 2))
+            n = 3 if k else 2
+            res = []
+            for rep in range(4):
+                t.reset()
+                res = [t.track_batch([frames[a:a + n]])[0] for a in range(0, 6, n)]
+            out[k] = np.concatenate(res)
+            t.close()
+        except Exception as e:  # surfaced below: an exception in a thread would otherwise only be a warning
+            errors[k] = repr(e)
 
     ths = [threading.Thread(target=work, args=(k,)) for k in range(2)]
     for th in ths:
@@ -261,8 +266,9 @@ def test_independent_handles_from_two_threads(pkg, small_seq):
     for th in ths:
         th.join(timeout=120)
     assert all(not th.is_alive() for th in ths)
+    assert errors == [None, None], errors
     for k in range(2):
-        assert np.array_equal(out[k].view(np.uint32), want.view(np.uint32))
+        assert np.array_equal(out[k].view(np.uint32), want.view(np.uint32)), f"thread {k}"
 
 
 def test_reciprocal_is_correctly_rounded_over_all_normals(pkg):
