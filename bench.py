@@ -80,7 +80,7 @@ def measured_peak():
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -88,11 +88,12 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.regions = []  # (label, wall-clock begin, end): the timed regions of the run
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25", "-i",
                  str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -101,42 +102,59 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append((time.perf_counter(), line.strip()))
+            self.lines.append(line.strip())
 
-    def mark_begin(self):
-        self.t_begin = time.perf_counter()
+    def mark_begin(self, label="device"):
+        self._open = (label, time.time())
 
     def mark_end(self):
-        self.t_end = time.perf_counter()
+        self.regions.append((self._open[0], self._open[1], time.time()))
+
+    @staticmethod
+    def _stamp(text):
+        # nvidia-smi prints its own sampling time ("2026/10/18 14:03:07.123", local time): samples are
+        # assigned to regions by that stamp, so pipe buffering cannot move them
+        import datetime
+
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
 
     def stop(self):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        self.t.join(timeout=2)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        t_begin, t_end = getattr(self, "t_begin", 0.0), getattr(self, "t_end", float("inf"))
-        for ts, ln in self.lines:
-            if ts < t_begin or ts > t_end + 0.1:
-                continue  # keep only samples taken during the timed region
+        rows = []
+        for ln in self.lines:
             parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
+            ts = self._stamp(parts[0])
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
+                rows.append((ts, float(parts[1]), float(parts[2]), [v.lower().startswith("active") for v in parts[4:8]]))
             except ValueError:
                 continue
-            for nm, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+
+        def pick(labels):
+            return [r for r in rows if r[0] is not None and
+                    any(lb in labels and b - 0.02 <= r[0] <= e + 0.02 for lb, b, e in self.regions)]
+
+        used = ["device"]
+        got = pick(used)
+        if len(got) < 3:  # a short device-resident region: take every timed region of the run (all under load)
+            used = sorted({lb for lb, _, _ in self.regions})
+            got = pick(used)
+        reasons = sorted({nm for r in got for nm, on in zip(names, r[3]) if on})
+        return {"sm_mhz": float(np.median([r[1] for r in got])) if got else None,
+                "sm_max_mhz": max(r[2] for r in got) if got else None,
+                "samples": len(got), "regions": used, "reasons": reasons}
 
 
 # --------------------------------------------------------------------------- CPU oracle arm
@@ -395,7 +413,6 @@ def run_ours(args):
     barrier()
     sampler.mark_end()
     launches = trk.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
         t = torch.tensor([ms_total], device=f"cuda:{local}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -443,10 +460,12 @@ def run_ours(args):
 
     run_pipelined(args.warmup)
     barrier()
+    sampler.mark_begin("e2e")
     t0 = time.perf_counter()
     run_pipelined(args.steps)
     trk.sync()
     e2e_s = time.perf_counter() - t0
+    sampler.mark_end()
     if dist is not None:
         torch.cuda.synchronize()
         t = torch.tensor([e2e_s], device=f"cuda:{local}")
@@ -459,11 +478,14 @@ def run_ours(args):
     for _ in range(args.warmup):
         step_e2e()
     barrier()
+    sampler.mark_begin("e2e_blocking")
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_e2e()
     trk.sync()
     blk_s = time.perf_counter() - t0
+    sampler.mark_end()
+    clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
         torch.cuda.synchronize()
         t = torch.tensor([blk_s], device=f"cuda:{local}")
