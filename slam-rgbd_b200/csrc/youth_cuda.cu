@@ -455,9 +455,11 @@ static RingGeom ring_of(const youth_cuda_handle* h, int n) {
 /* one iteration of the pairs ip.f0 .. ip.f0 + ip.fn - 1 of every sequence (`pairs` = S * fn) on stream q.
  * Few pairs per launch (live / frame-to-model): the latency of the tail matters, share it between the warps
  * of the last CTA; many pairs: no block barrier, the tails of different pairs overlap anyway. */
-static void launch_icp_on(youth_cuda_handle* h, const IcpParams& ip, int pairs, int level, cudaStream_t q) {
-  const dim3 grid((h->nruns[level] + YK_ICP_WARPS - 1) / YK_ICP_WARPS, pairs);
-  if ((long long)grid.x * pairs <= YK_ICP_LAST_CTA_MAX_CTAS)
+static void launch_icp_on(youth_cuda_handle* h, const IcpParams& ip, int fn, int level, cudaStream_t q) {
+  /* grid = (CTAs of a pair, frames of the range, sequences): the kernel reads its pair off blockIdx without a
+   * division (the division's live range cost k_icp eight spill instructions per two pixels) */
+  const dim3 grid((h->nruns[level] + YK_ICP_WARPS - 1) / YK_ICP_WARPS, fn, h->S);
+  if ((long long)grid.x * fn * h->S <= YK_ICP_LAST_CTA_MAX_CTAS)
     k_icp<false, true><<<grid, 32 * YK_ICP_WARPS, 0, q>>>(ip);
   else
     k_icp<false, false><<<grid, 32 * YK_ICP_WARPS, 0, q>>>(ip);
@@ -606,10 +608,10 @@ static int enqueue_icp_range(youth_cuda_handle* h, int n, int f0, int fn) {
         for (int it = 0; it < c.iters[level]; ++it) {
           if (K > 1) {
             h->launches++;
-            launch_icp_on(h, ip, h->S * gn, level, h->icp_q[g % K]);
+            launch_icp_on(h, ip, gn, level, h->icp_q[g % K]);
           } else {
             ProfScope ps(h, YOUTH_PROF_ICP0 + level);
-            launch_icp_on(h, ip, h->S * gn, level, h->stream);
+            launch_icp_on(h, ip, gn, level, h->stream);
           }
         }
       }
@@ -627,7 +629,7 @@ static int enqueue_icp_range(youth_cuda_handle* h, int n, int f0, int fn) {
       ip.fn = fn;
       for (int it = 0; it < c.iters[level]; ++it) {
         ProfScope ps(h, YOUTH_PROF_ICP0 + level);
-        launch_icp_on(h, ip, h->S * fn, level, h->stream);
+        launch_icp_on(h, ip, fn, level, h->stream);
       }
     }
   }

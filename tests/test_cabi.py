@@ -166,3 +166,19 @@ def test_product_never_references_the_oracle():
                     if re.search(r"oracle|yo_track|yo_icp", txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_dominant_kernel_keeps_its_register_budget(pkg):
+    """ptxas report of the build (lib/ptxas.log): the many-pairs k_icp variant stays at 96 registers
+    (5 CTAs per SM) without a stack frame.  A harmless-looking index change (a division whose result lived
+    across the pixel loop) once put eight spill instructions into the loop and cost 7 % of the step."""
+    log = os.path.join(os.path.dirname(pkg.lib_paths()["cuda"]), "ptxas.log")
+    if not os.path.exists(log):
+        pytest.skip("library was not built by the in-tree Makefile (no ptxas.log)")
+    text = open(log).read()
+    m = re.search(r"Function properties for _Z5k_icpILb0ELb0EEv9IcpParams\s*\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores, "
+                  r"(\d+) bytes spill loads\s*\n.*?Used (\d+) registers", text)
+    assert m, "k_icp<false,false> not found in ptxas.log"
+    stack, st, ld, regs = map(int, m.groups())
+    assert (stack, st, ld) == (0, 0, 0), f"k_icp spills: {stack} B stack, {st} B stores, {ld} B loads"
+    assert regs <= 96
