@@ -88,6 +88,11 @@ struct youth_cuda_handle {
   uint64_t ticket_next;
   int host_range; /* YOUTH_HOST_RANGE: frames per tracking range of host-fed groups (0 = whole group, see host_range_frames) */
   bool ingest_generic; /* YOUTH_INGEST_GENERIC=1: force the per-tap-product bilateral (A/B runs, tests) */
+  /* k_icp_fused: the whole iteration schedule of a few pairs in one launch (YOUTH_ICP_FUSED=1 turns it on,
+   * YOUTH_ICP_FUSED_COOP=0 launches it without the cooperative attribute) */
+  bool fused, fused_coop;
+  int fused_max_ctas;  /* CTAs of k_icp_fused the device holds at once */
+  unsigned int* gen;   /* [P] per-pair generation counters, zero between launches */
   /* pair state */
   double* pose_d;
   float* pose_f;
@@ -255,6 +260,7 @@ extern "C" void youth_cuda_destroy(youth_cuda_handle* h) {
   cudaFree(h->sums);
   cudaFree(h->pair_status);
   cudaFree(h->tickets);
+  cudaFree(h->gen);
   cudaFree(h->seq_count);
   cudaFree(h->world);
   cudaFree(h->traj);
@@ -395,6 +401,19 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
   CU(dalloc(&h->sums, (size_t)h->P * 32));
   CU(dalloc(&h->pair_status, (size_t)h->P));
   CU(dalloc(&h->tickets, (size_t)h->P));
+  CU(dalloc(&h->gen, (size_t)h->P));
+  {
+    const char* f = getenv("YOUTH_ICP_FUSED");
+    h->fused = f && *f == '1'; /* measured slower than one launch per iteration (profiles/README.md): opt-in */
+    const char* fc = getenv("YOUTH_ICP_FUSED_COOP");
+    h->fused_coop = !(fc && *fc == '0');
+    int per_sm = 0, sms = 0, coop = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_fused, 32 * YK_ICP_WARPS, 0));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
+    CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device));
+    h->fused_max_ctas = per_sm * sms;
+    if (!coop) h->fused_coop = false;
+  }
   CU(dalloc(&h->seq_count, (size_t)h->S));
   CU(dalloc(&h->world, (size_t)h->S * 12));
   CU(dalloc(&h->traj, (size_t)h->S * cfg->traj_capacity * 12));
@@ -463,6 +482,74 @@ static void launch_icp_on(youth_cuda_handle* h, const IcpParams& ip, int fn, int
     k_icp<false, true><<<grid, 32 * YK_ICP_WARPS, 0, q>>>(ip);
   else
     k_icp<false, false><<<grid, 32 * YK_ICP_WARPS, 0, q>>>(ip);
+}
+
+/* grid of one k_icp_fused launch over fn frames of every sequence, 0 when the fused kernel does not apply:
+ * turned off, a profiled step (per-level launch times are wanted), no iterations, or more CTAs than the
+ * device holds at once (the CTAs of a pair wait for each other inside the kernel) */
+static int fused_grid_x(const youth_cuda_handle* h, int fn) {
+  if (!h->fused || h->prof_on) return 0;
+  int gx = 0;
+  for (int l = 0; l < h->cfg.levels; ++l)
+    if (h->cfg.iters[l] > 0) {
+      const int c = (h->nruns[l] + YK_ICP_WARPS - 1) / YK_ICP_WARPS;
+      if (c > gx) gx = c;
+    }
+  /* Launches captured into a CUDA graph (live frames, frame-to-model) and launches without the cooperative
+   * attribute have no residency guarantee from the driver: they stay below half of the device, so that the
+   * fused launches of two handles running at once still fit together. */
+  const bool guaranteed = h->fused_coop && !(h->graphs_enabled && (h->m.on || fn <= YK_GRAPH_MAX_N));
+  const long long cap = guaranteed ? h->fused_max_ctas : h->fused_max_ctas / 2;
+  if (gx == 0 || (long long)gx * fn * h->S > cap) return 0;
+  return gx;
+}
+
+/* all iterations of all levels for frames [f0, f0 + fn) of every sequence's group, one launch on stream q */
+static int launch_icp_fused(youth_cuda_handle* h, const RingGeom& ring, int gx, int f0, int fn, cudaStream_t q) {
+  const youth_cuda_config& c = h->cfg;
+  IcpFusedParams fp;
+  memset(&fp, 0, sizeof(fp));
+  for (int level = c.levels - 1; level >= 0; --level) {
+    if (c.iters[level] <= 0) continue;
+    IcpFusedLevel& L = fp.lv[fp.nlv++];
+    L.maps = h->maps[level];
+    L.model = h->m.on ? h->m.maps[level] : NULL;
+    L.g = h->lv[level];
+    L.npix = h->npix[level];
+    L.ppr = h->ppr[level];
+    L.nruns = h->nruns[level];
+    L.iters = c.iters[level];
+  }
+  fp.ring = ring;
+  fp.max_runs = h->max_runs;
+  fp.dist2_thr = c.dist_thresh_m * c.dist_thresh_m;
+  fp.cos_thr = c.cos_thresh;
+  fp.pose_f = h->pose_f;
+  fp.pose_d = h->pose_d;
+  fp.seq_count = h->seq_count;
+  fp.partials = h->partials;
+  fp.tickets = h->tickets;
+  fp.gen = h->gen;
+  fp.sums = h->sums;
+  fp.pair_status = h->pair_status;
+  fp.min_inliers = c.min_inliers;
+  fp.f0 = f0;
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3(gx, fn, h->S);
+  lc.blockDim = dim3(32 * YK_ICP_WARPS);
+  lc.stream = q;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative; /* every CTA resident at once, or the launch waits its turn */
+  at[0].val.cooperative = 1;
+  lc.attrs = at;
+  lc.numAttrs = h->fused_coop ? 1 : 0;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  CU(cudaStreamIsCapturing(q, &cap));
+  if (cap != cudaStreamCaptureStatusNone) lc.numAttrs = 0; /* graph nodes: plain launch, see fused_grid_x */
+  h->launches++;
+  CU(cudaLaunchKernelEx(&lc, k_icp_fused, fp));
+  return 1;
 }
 
 static IcpParams icp_params(const youth_cuda_handle* h, int level, const RingGeom& ring) {
@@ -601,6 +688,10 @@ static int enqueue_icp_range(youth_cuda_handle* h, int n, int f0, int fn) {
     }
     for (int g = 0; g < ngroups; ++g) {
       const int gn = (g + 1) * G <= fn ? G : fn - g * G;
+      if (const int gx = fused_grid_x(h, gn)) {
+        if (!launch_icp_fused(h, ring, gx, f0 + g * G, gn, K > 1 ? h->icp_q[g % K] : h->stream)) return 0;
+        continue;
+      }
       for (int level = c.levels - 1; level >= 0; --level) {
         IcpParams ip = icp_params(h, level, ring);
         ip.f0 = f0 + g * G;
@@ -622,6 +713,8 @@ static int enqueue_icp_range(youth_cuda_handle* h, int n, int f0, int fn) {
         CU(cudaEventRecord(h->icp_join[k], h->icp_q[k]));
         CU(cudaStreamWaitEvent(h->stream, h->icp_join[k], 0));
       }
+  } else if (const int gx = fused_grid_x(h, fn)) {
+    if (!launch_icp_fused(h, ring, gx, f0, fn, h->stream)) return 0;
   } else {
     for (int level = c.levels - 1; level >= 0; --level) {
       IcpParams ip = icp_params(h, level, ring);

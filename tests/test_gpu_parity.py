@@ -364,3 +364,30 @@ def test_two_groups_in_flight_give_the_blocking_results(pkg, small_seq):
     for p in res + [pin]:
         trk.lib.youth_cuda_host_free(p)
     trk.close()
+
+
+@pytest.mark.parametrize("fused", ["1", "0"])
+@pytest.mark.parametrize("iters", [(10, 5, 4), (3, 0, 2), (0, 0, 3)])
+def test_fused_and_per_iteration_icp_match_the_oracle(pkg, oracle, small_seq, fused, iters, monkeypatch):
+    """YOUTH_ICP_FUSED=1: few pairs per launch take k_icp_fused (the whole coarse-to-fine schedule in one
+    launch, the CTAs of a pair handing over through a generation counter) instead of one k_icp launch per
+    iteration (the default: measured faster).  Both must give the oracle's poses and status words bit for
+    bit, also when a level has no iterations, over several groups (the counters are left zero) and for two
+    sequences in one launch."""
+    monkeypatch.setenv("YOUTH_ICP_FUSED", fused)
+    frames, _ = small_seq
+    other = pkg.synth_sequence(6, sequence=3)
+    trk = make_tracker(pkg, batch=2, n_streams=2, iters=list(iters) + [0])
+    ocfg = oracle.config_from(trk.cfg)
+    got = [[], []]
+    for g in range(3):
+        out = trk.track_batch([frames[2 * g:2 * g + 2], other[2 * g:2 * g + 2]])
+        for s in range(2):
+            got[s].append(out[s])
+    for s, seq in enumerate((frames, other)):
+        poses_o, st_o, inl_o = oracle.track_sequence(ocfg, seq)
+        poses_g = np.concatenate(got[s])
+        assert np.array_equal(poses_g.view(np.uint32), poses_o.view(np.uint32)), f"sequence {s}: poses not bit-identical"
+        _, _, st = trk.trajectory(s)
+        assert np.array_equal(st, st_o)
+    trk.close()
