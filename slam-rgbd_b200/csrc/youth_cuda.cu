@@ -83,6 +83,7 @@ struct youth_cuda_handle {
   /* bilateral tables */
   float ws[49];
   float* wr;
+  float* wt; /* product table of the bilateral (IngestParams.wt) */
   int range_cut;
   cudaEvent_t ticket_ev[YK_TICKETS]; /* youth_cuda_read_trajectory_async / youth_cuda_wait_ticket */
   uint64_t ticket_next;
@@ -254,6 +255,7 @@ extern "C" void youth_cuda_destroy(youth_cuda_handle* h) {
       if (h->chunk_ready[k][c2]) cudaEventDestroy(h->chunk_ready[k][c2]);
   }
   cudaFree(h->wr);
+  cudaFree(h->wt);
   cudaFree(h->pose_d);
   cudaFree(h->pose_f);
   cudaFree(h->partials);
@@ -394,6 +396,17 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
     wr[cut + 1] = 0.0f;
     CU(dalloc(&h->wr, (size_t)YK_RANGE_LUT_MAX));
     CU(cudaMemcpy(h->wr, wr, sizeof(float) * (cut + 2), cudaMemcpyHostToDevice));
+    /* product table of k_ingest<YK_INGEST_BILATERAL_WT>: one IEEE single-precision multiply per entry, the
+     * product the generic path (and the CPU statement) forms per tap */
+    CU(dalloc(&h->wt, (size_t)YK_WT_ROWS * YK_WT_STRIDE));
+    if (cut + 2 <= YK_WT_STRIDE) {
+      float wt[YK_WT_ROWS * YK_WT_STRIDE];
+      for (int row = 0; row < YK_WT_ROWS; ++row) {
+        const float w = h->ws[(row / 4 + 3) * 7 + (row % 4) + 3]; /* class (|dy|, |dx|) = (row / 4, row % 4) */
+        for (int i = 0; i < YK_WT_STRIDE; ++i) wt[row * YK_WT_STRIDE + i] = i < cut + 2 ? w * wr[i] : 0.0f;
+      }
+      CU(cudaMemcpy(h->wt, wt, sizeof(wt), cudaMemcpyHostToDevice));
+    }
   }
   CU(dalloc(&h->pose_d, (size_t)h->P * 12));
   CU(dalloc(&h->pose_f, (size_t)h->P * 12));
@@ -619,8 +632,7 @@ static int enqueue_preprocess(youth_cuda_handle* h, const uint16_t* const* raw_d
     ip.pyr_thr = 3.0f * c.sigma_range_mm;
     dim3 grid((c.width + YK_TILE_W - 1) / YK_TILE_W, (c.height + YK_TILE_H - 1) / YK_TILE_H, frames);
     ProfScope ps(h, YOUTH_PROF_INGEST);
-    for (int dy = 0; dy < 4; ++dy)
-      for (int dx = 0; dx < 4; ++dx) ip.ws16[dy * 4 + dx] = h->ws[(dy + 3) * 7 + dx + 3];
+    ip.wt = reinterpret_cast<const float4*>(h->wt);
     if (!c.bilateral)
       k_ingest<YK_INGEST_RAW><<<grid, 256, 0, h->stream>>>(ip);
     else if (h->range_cut + 2 <= YK_WT_STRIDE && !h->ingest_generic)
