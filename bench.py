@@ -587,7 +587,7 @@ def run_ours(args):
     ing_gbs = b_pre * ing_frames / (ing_ms * 1e-3) / 1e9 if ing_ms > 0 else 0.0
     ingest_roof = {"bound": "hbm", "kernel": "k_ingest + k_normals", "achieved": ing_gbs, "peak": peak, "unit": "GB/s",
                    "frac": ing_gbs / peak, "algorithmic_bytes_per_frame": b_pre,
-                   "note": "bounded by shared-memory wavefronts of the 49-tap bilateral (ncu: 90 % of the LSU data-pipe peak, "
+                   "note": "bounded by shared-memory wavefronts of the 49-tap bilateral (ncu: 87 % of the LSU data-pipe peak, "
                            "78 % issue utilisation), not by HBM"}
 
     traffic = None  # ncu DRAM bytes per launch: only valid for the configuration it was captured on
