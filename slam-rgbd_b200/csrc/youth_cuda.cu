@@ -677,6 +677,21 @@ static int host_range_frames(const youth_cuda_handle* h, int n_frames, int chunk
   return r >= n_frames ? n_frames : r;
 }
 
+/* Frames per copy + preprocess chunk of a host-fed group.  A caller that waits for every group wants small
+ * chunks (ingest of chunk c runs under the H2D of chunk c + 1, the tail after the last copy is one small
+ * chunk).  A caller that keeps two groups in flight (ticket API) has this group's copies hidden under the
+ * previous group's kernels anyway, and 19 ingest launches of 16 frames (4 800 CTAs = 4.05 waves each) waste
+ * a fifth of their last wave: when the previous group is still running, a quarter of the group per chunk. */
+static int host_chunk_frames(youth_cuda_handle* h, int n_frames, int k) {
+  int ch = (n_frames + YK_MAX_CHUNKS - 1) / YK_MAX_CHUNKS;
+  if (ch < YK_CHUNK_FRAMES) ch = YK_CHUNK_FRAMES;
+  if (h->host_range <= 0 && h->raw_used[k ^ 1] && cudaEventQuery(h->raw_free[k ^ 1]) == cudaErrorNotReady) {
+    const int big = (n_frames + 3) / 4;
+    if (big > ch) ch = big;
+  }
+  return ch;
+}
+
 /* stages 3-5 for frames [f0, f0 + fn) of every stream's group of n frames: coarse to fine, fixed iteration
  * schedule, one launch per iteration, no host sync.  Pairs are independent, so a group may be tracked in
  * several frame ranges (host-fed groups: the first range iterates while later frames are still in flight);
@@ -1047,8 +1062,7 @@ extern "C" int youth_cuda_track_batch(youth_cuda_handle* h, const uint16_t* cons
     } else {
       /* copy and preprocess in chunks: the H2D of chunk c+1 overlaps ingest of chunk c; and track in
        * frame ranges: stages 3-5 of range r iterate while the copy stream brings in range r+1 */
-      int ch = (n_frames + YK_MAX_CHUNKS - 1) / YK_MAX_CHUNKS;
-      if (ch < YK_CHUNK_FRAMES) ch = YK_CHUNK_FRAMES;
+      const int ch = host_chunk_frames(h, n_frames, k);
       const int range = host_range_frames(h, n_frames, ch);
       for (int s = 0; s < h->S; ++s) dev_ptrs[s] = h->raw[k] + (size_t)s * n_frames * frame_px;
       int ci = 0, tracked = 0;
@@ -1160,8 +1174,7 @@ extern "C" int youth_cuda_track_batch_packed(youth_cuda_handle* h, const uint8_t
   const size_t frame_px = (size_t)h->cfg.width * h->cfg.height;
   const uint16_t* dev_ptrs[YK_MAX_STREAMS];
   for (int s = 0; s < h->S; ++s) dev_ptrs[s] = h->raw[k] + (size_t)s * n_frames * frame_px;
-  int ch = (n_frames + YK_MAX_CHUNKS - 1) / YK_MAX_CHUNKS;
-  if (ch < YK_CHUNK_FRAMES) ch = YK_CHUNK_FRAMES;
+  const int ch = host_chunk_frames(h, n_frames, k);
   const int range = host_range_frames(h, n_frames, ch);
   int ci = 0, tracked = 0;
   for (int f0 = 0; f0 < n_frames; f0 += ch, ++ci) {
