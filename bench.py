@@ -274,7 +274,7 @@ def run_reference(args):
     import youth_pkg
 
     pkg = youth_pkg.load()
-    cfg = pkg.default_config()
+    cfg = pkg.default_config(**({"icp_ppt": args.ppt} if args.ppt else {}))
     threads = max(1, min(host_threads(), 64))
     fpt = 11  # 10 frame pairs per thread per step: a bounded sample of the 300-frame workload
     frames = pkg.synth_sequence(FRAMES)
@@ -603,7 +603,7 @@ def run_ours(args):
     streaming = None
     if (Wd, Hd, S) == (W, H, 1) and args.mode != "model":
         live = B.Tracker(pkg.default_config(batch=1, device=local, traj_capacity=128, levels=args.levels,
-                                            **({"icp_ppt": args.ppt} if args.ppt else {})))
+                                            **({"icp_ppt": args.user_ppt} if args.user_ppt else {})))
         for i in range(8):
             live.track(frames[0][i], ts=33 * i)
         t0 = time.perf_counter()
@@ -619,10 +619,12 @@ def run_ours(args):
     # thread (synchronous copy into the pinned host ring, SLAM.cpp:133-134), worker thread with two runs of
     # 64 frames in flight, youthSlamDrain + trajectory read-back at the end of every pass
     facade = None
-    if (Wd, Hd, S) == (W, H, 1) and args.mode != "model" and args.levels == 3 and not args.ppt:
+    if (Wd, Hd, S) == (W, H, 1) and args.mode != "model" and args.levels == 3:
         try:
             os.environ["YOUTH_SLAM_DEVICE"] = str(local)
             os.environ["YOUTH_SLAM_TRAJ_CAPACITY"] = str(FRAMES)
+            if args.ppt:
+                os.environ["YOUTH_SLAM_ICP_PPT"] = str(args.ppt)  # same reduction geometry as the device arm
             host = pkg.host_lib()
             host.youthSlamSetOptions(1, 64)  # lossless, 64 frames per launch group (the facade's maximum)
             host.initSlamModule(None, None)
@@ -726,6 +728,13 @@ def main():
                     help="frame = frame-to-frame (the headline workload), model = frame-to-model (TSDF fusion + ray cast)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.user_ppt = args.ppt
+    if not args.ppt and args.mode == "frame" and args.batch * args.sequences_per_gpu >= 64:
+        # launches of many pairs: longer ICP runs (75 runs = 19 CTAs per pair at every level instead of 150 / 38)
+        # amortise the per-CTA prologue and tail; measured on B200: 5.89 vs 6.19 ms of k_icp per 300-frame step,
+        # 256 is slower again (4.05 waves at level 0).  icp_ppt is part of the configuration the CPU statement
+        # follows, so both arms use it.
+        args.ppt = 128
     claim_stdout()
     if args.impl == "reference":
         return run_reference(args)

@@ -177,6 +177,8 @@ void initSlamModule(const char* config_file, const char* vocabulary_file) {
   G.cfg.batch = G.batch;
   const char* cap = getenv("YOUTH_SLAM_TRAJ_CAPACITY");
   G.cfg.traj_capacity = cap ? atoi(cap) : 65536;
+  const char* ppt = getenv("YOUTH_SLAM_ICP_PPT"); /* reduction geometry (youth_cuda_config.icp_ppt), validated by init */
+  if (ppt && atoi(ppt) > 0) G.cfg.icp_ppt = atoi(ppt);
   if (!youth_cuda_init(&G.cfg, &G.h)) {
     fprintf(stderr, "AlgorithmModule: failed to initialise the CUDA tracker: %s\n", youth_cuda_last_error());
     G.h = NULL;

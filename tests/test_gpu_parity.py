@@ -100,11 +100,13 @@ def test_icp_sums_and_correspondences(pkg, oracle, small_seq, ppt):
     trk.close()
 
 
-def test_track_sequence_pose_parity(pkg, oracle, small_seq):
+@pytest.mark.parametrize("ppt", [64, 128])
+def test_track_sequence_pose_parity(pkg, oracle, small_seq, ppt):
     """stages 1-5 end to end over 6 frames: poses vs oracle within 1e-4 m / 1e-4 rad (and,
-    by construction, bit-identical), inlier count identical."""
+    by construction, bit-identical), inlier count identical.  icp_ppt 64 = library default, 128 = what
+    bench.py uses for launches of many pairs."""
     frames, gt = small_seq
-    trk = make_tracker(pkg, batch=4)
+    trk = make_tracker(pkg, batch=4, icp_ppt=ppt)
     ocfg = oracle.config_from(trk.cfg)
     poses_g = np.concatenate([trk.track_batch([frames[:4]])[0], trk.track_batch([frames[4:6]])[0]])
     poses_o, st_o, _ = oracle.track_sequence(ocfg, frames)
