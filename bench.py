@@ -594,7 +594,8 @@ def run_ours(args):
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
-        if (Wd, Hd, S, args.levels) == (W, H, 1, 3) and tj.get("pairs_per_launch") == args.batch and args.mode == "frame":
+        if ((Wd, Hd, S, args.levels) == (W, H, 1, 3) and tj.get("pairs_per_launch") == args.batch and args.mode == "frame"
+                and tj.get("icp_ppt", 64) == (args.ppt or 64)):
             traffic = tj.get("k_icp_L0_dram_bytes_per_launch")
     except Exception:
         pass
