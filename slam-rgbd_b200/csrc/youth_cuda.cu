@@ -84,6 +84,9 @@ struct youth_cuda_handle {
   float ws[49];
   float* wr;
   float* wt; /* product table of the bilateral (IngestParams.wt) */
+  /* YK_FAST_DIV builds: reciprocal form of the vertex divisions, used when the exhaustive device check passed */
+  int fast_div;
+  float r_df, r_fx[YOUTH_MAX_LEVELS], r_fy[YOUTH_MAX_LEVELS];
   int range_cut;
   cudaEvent_t ticket_ev[YK_TICKETS]; /* youth_cuda_read_trajectory_async / youth_cuda_wait_ticket */
   uint64_t ticket_next;
@@ -408,6 +411,37 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
       CU(cudaMemcpy(h->wt, wt, sizeof(wt), cudaMemcpyHostToDevice));
     }
   }
+  h->fast_div = 0;
+#if YK_FAST_DIV
+  {
+    /* The dividends of the vertex divisions are d in [1, 65535], and (u - c) * z with z = d / depth_factor:
+     * with the bounds below they are 0 or lie in [2^-53, 2^51], inside the range k_div_check covers. */
+    const float df = cfg->depth_factor;
+    bool ok = df >= 0x1p-20f && df <= 0x1p20f && !getenv("YOUTH_NO_FAST_DIV");
+    unsigned long long* d_bad = NULL;
+    unsigned long long bad = 0;
+    CU(cudaMalloc((void**)&d_bad, sizeof(bad)));
+    CU(cudaMemset(d_bad, 0, sizeof(bad)));
+    h->r_df = 1.0f / df;
+    if (ok) k_div_check<<<148 * 8, 256>>>(df, h->r_df, d_bad);
+    for (int l = 0; l < cfg->levels && ok; ++l) {
+      const LevelGeom& g = h->lv[l];
+      ok = ok && g.fx >= 0x1p-10f && g.fx <= 0x1p20f && g.fy >= 0x1p-10f && g.fy <= 0x1p20f &&
+           (g.cx == 0.0f || (fabsf(g.cx) >= 0x1p-10f && fabsf(g.cx) <= 0x1p20f)) &&
+           (g.cy == 0.0f || (fabsf(g.cy) >= 0x1p-10f && fabsf(g.cy) <= 0x1p20f));
+      h->r_fx[l] = 1.0f / g.fx;
+      h->r_fy[l] = 1.0f / g.fy;
+      if (ok) {
+        k_div_check<<<148 * 8, 256>>>(g.fx, h->r_fx[l], d_bad);
+        k_div_check<<<148 * 8, 256>>>(g.fy, h->r_fy[l], d_bad);
+      }
+    }
+    CU(cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost));
+    cudaFree(d_bad);
+    CU(cudaGetLastError());
+    h->fast_div = ok && bad == 0 ? 1 : 0;
+  }
+#endif
   CU(dalloc(&h->pose_d, (size_t)h->P * 12));
   CU(dalloc(&h->pose_f, (size_t)h->P * 12));
   CU(dalloc(&h->partials, (size_t)h->P * h->max_runs * 32));
@@ -633,6 +667,14 @@ static int enqueue_preprocess(youth_cuda_handle* h, const uint16_t* const* raw_d
     dim3 grid((c.width + YK_TILE_W - 1) / YK_TILE_W, (c.height + YK_TILE_H - 1) / YK_TILE_H, frames);
     ProfScope ps(h, YOUTH_PROF_INGEST);
     ip.wt = reinterpret_cast<const float4*>(h->wt);
+#if YK_FAST_DIV
+    ip.fast_div = h->fast_div;
+    ip.r_df = h->r_df;
+    for (int l = 0; l < c.levels; ++l) {
+      ip.r_fx[l] = h->r_fx[l];
+      ip.r_fy[l] = h->r_fy[l];
+    }
+#endif
     if (!c.bilateral)
       k_ingest<YK_INGEST_RAW><<<grid, 256, 0, h->stream>>>(ip);
     else if (h->range_cut + 2 <= YK_WT_STRIDE && !h->ingest_generic)
