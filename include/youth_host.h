@@ -9,6 +9,7 @@
  *   youth_bin_read_frame   <- readFrameFromFile   loggingModule.c:404-444
  *   youth_chunk_*          <- sendDataInChunks    loggingModule.c:447-485 / sensorModule.c:149-210
  *   youth_reasm_*          <- loggerThread reassembly + completion test   loggingModule.c:292-357
+ *   youth_mq_consume       <- the viewer's receive loop   ViewerModule/viewerModule.c:160-250 (dataReceiveThread)
  *   youth_config_from_yaml <- cv::FileStorage keys read by ORB-SLAM3 from
  *                             AlgorithmModule/config/astra_orb_slam3_rgbd.yaml:9-20,35
  *   youth_tum_write        <- SaveTrajectoryTUM call site   AlgorithmModule/SLAM.cpp:187-188
@@ -63,6 +64,15 @@ int youth_reasm_feed(youth_reasm* r, const void* msg, size_t len);
 const uint16_t* youth_reasm_depth(const youth_reasm* r);
 const uint8_t* youth_reasm_color(const youth_reasm* r);
 void youth_reasm_info(const youth_reasm* r, int* width, int* height, int* frame_id, uint32_t* timestamp_ms);
+
+/* Viewer-side queue consumer (the queue the logger's pass-through and playbackThread write,
+ * loggingModule.c:284-288, :584-590; reader in the reference: viewerModule.c:160-250).  Opens `queue`
+ * (e.g. MQ_LOGGER_TO_VIEWER) read-only, reassembles frames and calls `sink` -- processSlamFrame or anything
+ * of its signature -- once per whole frame, on the calling thread.  Returns when *stop becomes non-zero
+ * (stop may be NULL), when no message arrived for idle_timeout_ms (<= 0: never), or when sink returns 0.
+ * Return value: frames delivered, -1 if the queue cannot be opened or read. */
+typedef int (*youth_frame_sink)(const int16_t* depth, const uint8_t* color, int width, int height, uint32_t timestamp_ms);
+long youth_mq_consume(const char* queue, youth_frame_sink sink, volatile int* stop, int idle_timeout_ms);
 
 /* ---------------------------------------------------------------- synthetic sequences */
 typedef struct youth_synth_config {

@@ -57,6 +57,8 @@ int ref_pipeline_start(void) {
   mq_unlink(MQ_SENSOR_TO_LOGGER);
   mq_unlink(MQ_LOGGER_TO_VIEWER);
   mq_unlink(MQ_CONTROL_QUEUE);
+  isPassThroughEnabled = 1; /* the module's statics as a fresh process has them (a finished playback leaves 0 behind) */
+  isPlaybackActive = 0;
   initLoggingModule(); /* loggingModule.c:616 */
   g_viewer_run = 1;
   g_viewer_msgs = 0;
@@ -79,6 +81,28 @@ int ref_fake_sensor_send(int frame_id, uint32_t ts, int width, int height, const
 
 long ref_viewer_messages(void) { return g_viewer_msgs; }
 
+/* ---- playback direction: the reference's playbackThread (loggingModule.c:505-611) writes a recording into
+ * MQ_LOGGER_TO_VIEWER; the test puts the product's queue consumer in the viewer's seat ---- */
+/* retire the fake viewer so that somebody else can read the viewer queue */
+void ref_viewer_stop(void) {
+  if (!g_viewer_run) return;
+  g_viewer_run = 0;
+  pthread_join(g_viewer, NULL);
+}
+/* the reference's own startPlayback (loggingModule.c:710-720) + sensor messages: the command sits in the
+ * control queue until loggerThread comes round to polling it, and loggerThread blocks on the sensor queue
+ * (SURVEY appendix A), so a metadata message wakes it */
+int ref_start_playback(const char* filename) {
+  if (!startPlayback(filename)) return 0;
+  mqd_t mq = mq_open(MQ_SENSOR_TO_LOGGER, O_WRONLY);
+  if (mq == (mqd_t)-1) return 0;
+  sendMetadata(mq, -1, 0, 8, 8);
+  sendMetadata(mq, -1, 0, 8, 8); /* the first one may be consumed before the command is in the control queue */
+  mq_close(mq);
+  return 1;
+}
+int ref_is_playing_back(void) { return isPlayingBack(); }
+
 /* orderly stop: the reference's loggerThread blocks in mq_receive on the sensor queue,
  * so the flag is cleared first and one metadata message wakes it up */
 void ref_pipeline_stop(void) {
@@ -89,8 +113,7 @@ void ref_pipeline_stop(void) {
     mq_close(mq);
   }
   stopLoggingModule(); /* loggingModule.c:668 */
-  g_viewer_run = 0;
-  pthread_join(g_viewer, NULL);
+  ref_viewer_stop();
   mq_unlink(MQ_SENSOR_TO_LOGGER);
   mq_unlink(MQ_LOGGER_TO_VIEWER);
   mq_unlink(MQ_CONTROL_QUEUE);

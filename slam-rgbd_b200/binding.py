@@ -178,6 +178,7 @@ def host_lib():
         "youth_reasm_color": (C.c_void_p, [C.c_void_p]),
         "youth_reasm_info": (None, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                     C.POINTER(C.c_uint32)]),
+        "youth_mq_consume": (C.c_long, [C.c_char_p, C.c_void_p, C.POINTER(C.c_int), C.c_int]),
         # facade (include/SLAM.h, algorithmModule.h)
         "initSlamModule": (None, [C.c_char_p, C.c_char_p]),
         "stopSlamModule": (None, []),

@@ -6,7 +6,10 @@
  * thread initialises the tracker and then either serves processSlamFrame() callers (the
  * Logging hook at loggingModule.c:354) until stopSlamModule(), or -- when `id` is a path --
  * replays a .bin recording headless, the way playbackThread does for the viewer
- * (loggingModule.c:542-594) but without the 30 fps pacing sleep.
+ * (loggingModule.c:542-594) but without the 30 fps pacing sleep, or -- when `id` is
+ * "mq:<queue name>" -- takes the viewer's seat on that queue (viewerModule.c:160-250): with
+ * "mq:/logger_viewer_queue" the tracker follows whatever the reference's logger passes through or its
+ * playbackThread replays (loggingModule.c:284-288, :584-590), with no change to the reference at all.
  */
 #define _GNU_SOURCE
 #include <stdio.h>
@@ -31,6 +34,17 @@ void* algorithmModule(void* id) {
   if (!isSlamModuleRunning()) return NULL;
   if (!replay) {
     while (isSlamModuleRunning()) usleep(10000);
+    return NULL;
+  }
+  if (strncmp(replay, "mq:", 3) == 0) {
+    const char* idle = getenv("YOUTH_SLAM_MQ_IDLE_MS"); /* leave after this long without a message (default 2 s) */
+    const long frames = youth_mq_consume(replay + 3, processSlamFrame, NULL, idle ? atoi(idle) : 2000);
+    if (frames < 0) fprintf(stderr, "algorithmModule: cannot read queue '%s'\n", replay + 3);
+    youthSlamDrain();
+    const char* out = getenv("YOUTH_SLAM_OUT");
+    if (out && frames > 0) saveSlamMap(out);
+    fprintf(stderr, "algorithmModule: tracked %ld frames from queue %s\n", frames, replay + 3);
+    stopSlamModule();
     return NULL;
   }
   FILE* f = fopen(replay, "rb");

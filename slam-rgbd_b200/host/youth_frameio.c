@@ -13,8 +13,13 @@
  * chunkIndex * 7900 (loggingModule.c:313); a frame is complete when the last depth chunk
  * AND the last colour chunk have been seen (loggingModule.c:354).
  */
+#define _GNU_SOURCE
+#include <errno.h>
+#include <fcntl.h>
+#include <mqueue.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "youth_host.h"
 
@@ -224,4 +229,54 @@ void youth_reasm_info(const youth_reasm* r, int* w, int* h, int* id, uint32_t* t
   if (h) *h = r->height;
   if (id) *id = r->frame_id;
   if (ts) *ts = r->timestamp;
+}
+
+/* Consumer of a viewer-side queue: the reference feeds MQ_LOGGER_TO_VIEWER from two places, the logger's
+ * pass-through (loggingModule.c:284-288) and playbackThread (loggingModule.c:584-590), and its only reader
+ * is the viewer's receive loop (viewerModule.c:160-250).  This is that loop for the tracker: receive,
+ * reassemble (same completion test as the logger, loggingModule.c:354), hand every whole frame to `sink`
+ * (the processSlamFrame signature) before the next message is received, so the reassembly buffer can be
+ * reused -- the callee copies, SLAM.cpp:133-134. */
+long youth_mq_consume(const char* queue, youth_frame_sink sink, volatile int* stop, int idle_timeout_ms) {
+  if (!queue || !sink) return -1;
+  mqd_t mq = mq_open(queue, O_RDONLY);
+  if (mq == (mqd_t)-1) return -1;
+  struct mq_attr attr;
+  if (mq_getattr(mq, &attr) != 0 || attr.mq_msgsize <= 0) {
+    mq_close(mq);
+    return -1;
+  }
+  char* buf = (char*)malloc((size_t)attr.mq_msgsize);
+  youth_reasm* r = youth_reasm_create();
+  long frames = buf && r ? 0 : -1;
+  int idle_ms = 0;
+  while (frames >= 0 && !(stop && *stop)) {
+    struct timespec to;
+    clock_gettime(CLOCK_REALTIME, &to);
+    to.tv_nsec += 20 * 1000 * 1000; /* poll period for `stop` */
+    if (to.tv_nsec >= 1000000000L) {
+      to.tv_sec += 1;
+      to.tv_nsec -= 1000000000L;
+    }
+    const ssize_t n = mq_timedreceive(mq, buf, (size_t)attr.mq_msgsize, NULL, &to);
+    if (n < 0) {
+      if (errno == EINTR) continue;
+      if (errno != ETIMEDOUT) {
+        frames = -1;
+        break;
+      }
+      idle_ms += 20;
+      if (idle_timeout_ms > 0 && idle_ms >= idle_timeout_ms) break;
+      continue;
+    }
+    idle_ms = 0;
+    if (youth_reasm_feed(r, buf, (size_t)n) == 1) { /* malformed messages (-1) are dropped, like the viewer does */
+      if (!sink((const int16_t*)r->depth, r->color, r->width, r->height, r->timestamp)) break;
+      ++frames;
+    }
+  }
+  youth_reasm_destroy(r);
+  free(buf);
+  mq_close(mq);
+  return frames;
 }

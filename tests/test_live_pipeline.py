@@ -32,6 +32,7 @@ def ref():
     L.ref_fake_sensor_send.argtypes = [C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.ref_hook_calls.restype = C.c_long
     L.ref_viewer_messages.restype = C.c_long
+    L.ref_start_playback.argtypes = [C.c_char_p]
     return L
 
 
@@ -71,6 +72,67 @@ def test_reference_logger_thread_reaches_the_hook_with_whole_frames(ref):
         assert (w, h, ts) == (gw, gh, gts) and np.array_equal(d, gd) and np.array_equal(c, gc)
     # pass-through to the viewer queue kept running: 1 metadata + depth + colour chunks per frame
     assert ref.ref_viewer_messages() >= 3 * (1 + 1 + 2) + (1 + 78 + 117)
+
+
+def test_reference_playback_thread_feeds_the_queue_consumer(pkg, ref, tmp_path):
+    """Playback direction: a recording (written by this repository's record writer) is replayed by the reference's
+    OWN playbackThread (loggingModule.c:505-611, started by its own startPlayback) into /logger_viewer_queue, where
+    youth_mq_consume sits in the viewer's seat (viewerModule.c:160-250) and hands whole frames to a
+    processSlamFrame-shaped sink: every frame arrives once, in order, bit-identical, sizes changing in between."""
+    import threading
+
+    host = pkg.host_lib()
+    rng = np.random.default_rng(5)
+    path = str(tmp_path / "rec.bin").encode()
+    sent = []
+    f = C.CDLL(None).fopen
+    f.restype, f.argtypes = C.c_void_p, [C.c_char_p, C.c_char_p]
+    fclose = C.CDLL(None).fclose
+    fclose.argtypes = [C.c_void_p]
+    host.youth_bin_write_frame.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    host.youth_bin_write_eof.argtypes = [C.c_void_p]
+    fp = f(path, b"wb")
+    for i, (w, h) in enumerate([(64, 48), (640, 480), (640, 480), (32, 24), (64, 48)]):  # 640x480 is the reader's 1 MiB limit
+        d = rng.integers(0, 9000, size=(h, w), dtype=np.uint16)
+        c = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        sent.append((d, c, w, h, 1000 + 33 * i))
+        assert host.youth_bin_write_frame(fp, i, 1000 + 33 * i, w, h, d.ctypes.data, c.ctypes.data) == 1
+    assert host.youth_bin_write_eof(fp) == 1
+    fclose(fp)
+
+    got = []
+
+    def sink(d, c, w, h, ts):
+        depth = np.ctypeslib.as_array(C.cast(d, C.POINTER(C.c_uint16)), shape=(h, w)).copy()
+        color = np.ctypeslib.as_array(C.cast(c, C.POINTER(C.c_uint8)), shape=(h, w, 3)).copy()
+        got.append((depth, color, w, h, ts))
+        return 1
+
+    cb_sink = PROCESS(sink)
+    cb_run, cb_proc = RUNNING(lambda: 0), PROCESS(lambda *a: 1)
+    ref.ref_hook_install(C.cast(cb_run, C.c_void_p), C.cast(cb_proc, C.c_void_p))
+    assert ref.ref_pipeline_start() == 1
+    stop = C.c_int(0)
+    result = {}
+    try:
+        ref.ref_viewer_stop()  # the consumer under test reads the viewer queue instead of the fake viewer
+        t = threading.Thread(
+            target=lambda: result.update(n=host.youth_mq_consume(b"/logger_viewer_queue", C.cast(cb_sink, C.c_void_p),
+                                                                 C.byref(stop), 0)))
+        t.start()
+        assert ref.ref_start_playback(path) == 1
+        assert wait_for(lambda: len(got) == len(sent))  # paced at 30 fps by the reference (loggingModule.c:593)
+        assert wait_for(lambda: ref.ref_is_playing_back() == 0)  # the EOF record ends the playback
+        stop.value = 1
+        t.join(timeout=10)
+        assert not t.is_alive()
+    finally:
+        stop.value = 1
+        ref.ref_pipeline_stop()
+    assert result["n"] == len(sent) == len(got)
+    for (d, c, w, h, ts), (gd, gc, gw, gh, gts) in zip(sent, got):
+        assert (w, h, ts) == (gw, gh, gts) and np.array_equal(d, gd) and np.array_equal(c, gc)
+    assert host.youth_mq_consume(b"/no_such_queue_here", C.cast(cb_sink, C.c_void_p), None, 100) == -1
 
 
 @pytest.mark.gpu
