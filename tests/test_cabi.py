@@ -20,6 +20,7 @@ def declared_functions(header):
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
     src = re.sub(r"typedef struct[^;]*?\{.*?\}\s*\w+;", "", src, flags=re.S)
+    src = re.sub(r"typedef\s+\w+\s*\(\s*\*\s*\w+\s*\)\s*\([^;]*\);", "", src)  # function-pointer typedefs
     names = [m.group(1) for m in DECL.finditer(src)]
     return [n for n in names if n not in ("YOUTH_STATIC_ASSERT",)]
 
