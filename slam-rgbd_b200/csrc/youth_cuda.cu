@@ -87,6 +87,7 @@ struct youth_cuda_handle {
   /* YK_FAST_DIV builds: reciprocal form of the vertex divisions, used when the exhaustive device check passed */
   int fast_div;
   float r_df, r_fx[YOUTH_MAX_LEVELS], r_fy[YOUTH_MAX_LEVELS];
+  int icp_xy; /* YK_ICP_XY builds: k_icp recomputes vx, vy (fast_div holds and the multiply-high pixel quotient is exact) */
   int range_cut;
   cudaEvent_t ticket_ev[YK_TICKETS]; /* youth_cuda_read_trajectory_async / youth_cuda_wait_ticket */
   uint64_t ticket_next;
@@ -442,6 +443,16 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
     h->fast_div = ok && bad == 0 ? 1 : 0;
   }
 #endif
+  h->icp_xy = 0;
+#if YK_ICP_XY
+  {
+    /* p / w == umulhi(p, ceil(2^32 / w)) for every p < npix when npix * w <= 2^32 */
+    bool ok = h->fast_div && !getenv("YOUTH_NO_ICP_XY");
+    for (int l = 0; l < cfg->levels; ++l)
+      ok = ok && h->lv[l].w >= 2 && (unsigned long long)h->npix[l] * (unsigned long long)h->lv[l].w <= (1ull << 32);
+    h->icp_xy = ok ? 1 : 0;
+  }
+#endif
   CU(dalloc(&h->pose_d, (size_t)h->P * 12));
   CU(dalloc(&h->pose_f, (size_t)h->P * 12));
   CU(dalloc(&h->partials, (size_t)h->P * h->max_runs * 32));
@@ -525,6 +536,15 @@ static void launch_icp_on(youth_cuda_handle* h, const IcpParams& ip, int fn, int
   /* grid = (CTAs of a pair, frames of the range, sequences): the kernel reads its pair off blockIdx without a
    * division (the division's live range cost k_icp eight spill instructions per two pixels) */
   const dim3 grid((h->nruns[level] + YK_ICP_WARPS - 1) / YK_ICP_WARPS, fn, h->S);
+#if YK_ICP_XY
+  if (h->icp_xy && ip.model == nullptr) { /* the previous frame's maps come from stage 2: vx, vy can be recomputed */
+    if ((long long)grid.x * fn * h->S <= YK_ICP_LAST_CTA_MAX_CTAS)
+      k_icp<false, true, YK_ICP_XY><<<grid, 32 * YK_ICP_WARPS, 0, q>>>(ip);
+    else
+      k_icp<false, false, YK_ICP_XY><<<grid, 32 * YK_ICP_WARPS, 0, q>>>(ip);
+    return;
+  }
+#endif
   if ((long long)grid.x * fn * h->S <= YK_ICP_LAST_CTA_MAX_CTAS)
     k_icp<false, true><<<grid, 32 * YK_ICP_WARPS, 0, q>>>(ip);
   else
@@ -628,6 +648,11 @@ static IcpParams icp_params(const youth_cuda_handle* h, int level, const RingGeo
   ip.model = h->m.on ? h->m.maps[level] : NULL;
   ip.f0 = 0;
   ip.fn = ring.n;
+#if YK_ICP_XY
+  ip.r_fx = h->r_fx[level];
+  ip.r_fy = h->r_fy[level];
+  ip.w_magic = (unsigned int)(((1ull << 32) + (unsigned long long)h->lv[level].w - 1) / (unsigned long long)h->lv[level].w);
+#endif
   return ip;
 }
 

@@ -19,13 +19,19 @@ __device__ __forceinline__ int gather_index(int p) {
 
 struct Rec { float4 a; float4 b; };
 
-// MODE 0: two float4 arrays (32 B/px/frame); MODE 2: three float2 planes (24 B/px/frame)
+// MODE 0: two float4 arrays (32 B/px/frame); MODE 2: three float2 planes (24 B/px/frame);
+// MODE 3: the same layout, planes 1 and 2 only (16 B/px/frame) -- what k_icp requests when it recomputes
+// vx, vy from vz (-DYK_ICP_XY=3)
 template <int MODE>
 __device__ __forceinline__ Rec load_rec(const float* f, int p) {
   Rec r;
   if (MODE == 0) {
     r.a = __ldg((const float4*)f + p);
     r.b = __ldg((const float4*)(f + (size_t)NPIX * 4) + p);
+  } else if (MODE == 3) {
+    const float2 y = __ldg((const float2*)(f + (size_t)NPIX * 2) + p), z = __ldg((const float2*)(f + (size_t)NPIX * 4) + p);
+    r.a = make_float4(y.x, y.y, z.x, z.y);
+    r.b = make_float4(0.f, 0.f, 0.f, 0.f);
   } else {
     const float2 x = __ldg((const float2*)f + p), y = __ldg((const float2*)(f + (size_t)NPIX * 2) + p),
                  z = __ldg((const float2*)(f + (size_t)NPIX * 4) + p);
@@ -79,7 +85,7 @@ __global__ void __launch_bounds__(128) k(const float* __restrict__ base, float* 
 
 template <int MODE, int SD, int GD>
 void run(const float* base, float* out, int ppr, int blocks_per_sm) {
-  const double bytes_per_px = MODE == 0 ? 64 : 48;
+  const double bytes_per_px = MODE == 0 ? 64 : (MODE == 3 ? 32 : 48);
   int maxb = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&maxb, k<MODE, SD, GD>, 128, 0));
   if (blocks_per_sm > maxb) return;
@@ -97,7 +103,7 @@ void run(const float* base, float* out, int ppr, int blocks_per_sm) {
   float ms; CK(cudaEventElapsedTime(&ms, a, b));
   const double us = ms * 1e3 / reps, gb = bytes_per_px * NPIX * PAIRS / 1e9;
   printf("%s SD=%d GD=%d ppr=%3d warps/SM=%2d (max %2d) %7.1f us/launch %6.0f GB/s requested\n",
-         MODE == 0 ? "float4x2 " : "3xfloat2 ", SD, GD, ppr, 4 * (blocks_per_sm < maxb ? blocks_per_sm : maxb), 4 * maxb, us,
+         MODE == 0 ? "float4x2 " : (MODE == 3 ? "2xfloat2 " : "3xfloat2 "), SD, GD, ppr, 4 * (blocks_per_sm < maxb ? blocks_per_sm : maxb), 4 * maxb, us,
          gb / (us * 1e-6));
 }
 
@@ -116,6 +122,8 @@ int main() {
       run<2, 2, 1>(base, out, ppr, bps);
       run<2, 2, 2>(base, out, ppr, bps);
       run<2, 3, 2>(base, out, ppr, bps);
+      run<3, 2, 2>(base, out, ppr, bps);
+      run<3, 3, 2>(base, out, ppr, bps);
     }
   }
   return 0;
