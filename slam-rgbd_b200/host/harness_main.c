@@ -4,6 +4,8 @@
  *
  *   youth_harness gen  <out.bin> <frames> [sequence] [width height]   write a synthetic recording + <out.bin>.gt.txt
  *   youth_harness run  <in.bin> <out_prefix>                          replay through algorithmModule(), write TUM files
+ *   youth_harness run  mq:/logger_viewer_queue <out_prefix>           track what the reference's logger / playbackThread put on
+ *                                                                     the viewer queue (until YOUTH_SLAM_MQ_IDLE_MS of silence)
  *   youth_harness pack <in.bin> <out.bin>                             transcode raw depth records to YD16-packed records (GPU codec)
  */
 #define _GNU_SOURCE
@@ -156,7 +158,7 @@ int main(int argc, char** argv) {
   else if (argc >= 2 && !strcmp(argv[1], "run")) rc = cmd_run(argc, argv);
   else if (argc >= 2 && !strcmp(argv[1], "pack")) rc = cmd_pack(argc, argv);
   if (rc == 2)
-    fprintf(stderr, "usage: %s gen <out.bin> <frames> [sequence] [w h] | run <in.bin> <out_prefix> | pack <in.bin> <out.bin>\n",
+    fprintf(stderr, "usage: %s gen <out.bin> <frames> [sequence] [w h] | run <in.bin | mq:/queue> <out_prefix> | pack <in.bin> <out.bin>\n",
             argv[0]);
   return rc;
 }
