@@ -5,9 +5,10 @@
  * [2^-64, 2^64), both signs.  Build and run:
  *   gcc -O2 -ffp-contract=off -fopenmp -mfma -o /tmp/exact_div_check tools/exact_div_check.c -lm && /tmp/exact_div_check
  * Result (8 host cores, 7.5 s): 0 mismatches of 2^31 for each of 570.3, 1000, 5000, 525, 531.5, 285.15, 142.575,
- * 1140.6 -- the intrinsics and depth factors of the test configurations.  Not wired into the kernels yet
- * (what comes next): it needs the same exhaustive check on the device at init for the configured
- * divisors, and a measurement. */
+ * 1140.6 -- the intrinsics and depth factors of the test configurations.  Wired into the kernels as compile-time
+ * options (-DYK_FAST_DIV=1: k_ingest, behind the same exhaustive check run on the device at init, k_div_check;
+ * -DYK_ICP_XY: k_icp recomputes vx, vy with it), both waiting for their first GPU measurement (DESIGN.md,
+ * what comes next). */
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
