@@ -235,6 +235,12 @@ void initSlamModule(const char* config_file, const char* vocabulary_file) {
     free(G.ts);
     youth_cuda_destroy(G.h);
     G.h = NULL;
+    G.ring = NULL;
+    G.ts = NULL;
+    if (G.pose_mq != (mqd_t)-1) {
+      mq_close(G.pose_mq);
+      G.pose_mq = (mqd_t)-1;
+    }
     return;
   }
   atomic_store(&G.running, 1);
@@ -248,7 +254,11 @@ void stopSlamModule(void) {
   pthread_cond_broadcast(&G.nonfull);
   pthread_mutex_unlock(&G.mu);
   pthread_join(G.worker, NULL); /* the worker drains what is queued before leaving */
+  /* a producer that passed the `running` test before stop_req was set either holds the mutex now (wait for it
+   * to leave the ring) or will see stop_req once it has it */
+  pthread_mutex_lock(&G.mu);
   atomic_store(&G.running, 0);
+  pthread_mutex_unlock(&G.mu);
   youth_cuda_destroy(G.h);
   G.h = NULL;
   youth_cuda_host_free(G.ring);
@@ -266,13 +276,13 @@ int processSlamFrame(const int16_t* depth_data, const uint8_t* color_data, int w
   if (!atomic_load(&G.running) || !G.h || !depth_data) return 0;
   if (width != G.cfg.width || height != G.cfg.height) return 0;
   pthread_mutex_lock(&G.mu);
-  if (G.lossless) {
+  if (G.lossless)
     while (G.count + G.busy >= G.qcap && !atomic_load(&G.stop_req)) pthread_cond_wait(&G.nonfull, &G.mu);
-    if (atomic_load(&G.stop_req)) {
-      pthread_mutex_unlock(&G.mu);
-      return 0;
-    }
-  } else if (G.count > QUEUE_HIGH_WATER || G.count + G.busy >= G.qcap) {
+  if (atomic_load(&G.stop_req)) { /* stopSlamModule() is under way: the ring is about to be released */
+    pthread_mutex_unlock(&G.mu);
+    return 0;
+  }
+  if (!G.lossless && (G.count > QUEUE_HIGH_WATER || G.count + G.busy >= G.qcap)) {
     /* SLAM.cpp:163-167: more than 10 waiting -> drop the oldest down to 5 */
     while (G.count > QUEUE_LOW_WATER) {
       G.head = (G.head + 1) % G.qcap;
