@@ -46,6 +46,7 @@ static struct {
   pthread_t worker;
   long accepted, dropped, tracked, poses_sent;
   atomic_int last_inliers;
+  atomic_int model_on; /* frame-to-model tracking (YOUTH_SLAM_MODE=model) */
   mqd_t pose_mq; /* optional pose egress to the viewer queue (MSG_TYPE_POSE), -1 = off */
 } G = {.mu = PTHREAD_MUTEX_INITIALIZER,
        .nonempty = PTHREAD_COND_INITIALIZER,
@@ -176,7 +177,7 @@ void initSlamModule(const char* config_file, const char* vocabulary_file) {
   G.cfg.n_streams = 1;
   G.cfg.batch = G.batch;
   const char* cap = getenv("YOUTH_SLAM_TRAJ_CAPACITY");
-  G.cfg.traj_capacity = cap ? atoi(cap) : 65536;
+  G.cfg.traj_capacity = cap ? atoi(cap) : (1 << 20); /* 9.7 h of 30 fps frames; 52 B per pose on the device */
   const char* ppt = getenv("YOUTH_SLAM_ICP_PPT"); /* reduction geometry (youth_cuda_config.icp_ppt), validated by init */
   if (ppt && atoi(ppt) > 0) G.cfg.icp_ppt = atoi(ppt);
   if (!youth_cuda_init(&G.cfg, &G.h)) {
@@ -188,6 +189,7 @@ void initSlamModule(const char* config_file, const char* vocabulary_file) {
     /* YOUTH_SLAM_MODE=model: track against a fused TSDF model instead of the previous frame
      * (include/youth_model.h) -- what TrackRGBD does with its map, SLAM.cpp:54 */
     const char* mode = getenv("YOUTH_SLAM_MODE");
+    atomic_store(&G.model_on, 0);
     if (mode && !strcmp(mode, "model")) {
       youth_tsdf_config tc;
       youth_tsdf_default_config(&tc);
@@ -197,6 +199,7 @@ void initSlamModule(const char* config_file, const char* vocabulary_file) {
         G.h = NULL;
         return;
       }
+      atomic_store(&G.model_on, 1);
     }
   }
   G.qcap = QUEUE_HIGH_WATER + 2 + 3 * G.batch; /* queue + the two runs in flight always fit */
@@ -258,13 +261,16 @@ void stopSlamModule(void) {
    * to leave the ring) or will see stop_req once it has it */
   pthread_mutex_lock(&G.mu);
   atomic_store(&G.running, 0);
-  pthread_mutex_unlock(&G.mu);
-  youth_cuda_destroy(G.h);
+  youth_cuda_handle* h = G.h; /* threads that waited for the idle worker under the mutex find no handle from here on */
+  uint16_t* ring = G.ring;
+  uint32_t* ts = G.ts;
   G.h = NULL;
-  youth_cuda_host_free(G.ring);
-  free(G.ts);
   G.ring = NULL;
   G.ts = NULL;
+  pthread_mutex_unlock(&G.mu);
+  youth_cuda_destroy(h);
+  youth_cuda_host_free(ring);
+  free(ts);
   if (G.pose_mq != (mqd_t)-1) {
     mq_close(G.pose_mq);
     G.pose_mq = (mqd_t)-1;
@@ -273,23 +279,31 @@ void stopSlamModule(void) {
 
 int processSlamFrame(const int16_t* depth_data, const uint8_t* color_data, int width, int height, uint32_t timestamp) {
   (void)color_data; /* depth-only tracker; colour passes through the pipeline untouched */
-  if (!atomic_load(&G.running) || !G.h || !depth_data) return 0;
+  if (!atomic_load(&G.running) || !depth_data) return 0;
   if (width != G.cfg.width || height != G.cfg.height) return 0;
   pthread_mutex_lock(&G.mu);
   if (G.lossless)
     while (G.count + G.busy >= G.qcap && !atomic_load(&G.stop_req)) pthread_cond_wait(&G.nonfull, &G.mu);
-  if (atomic_load(&G.stop_req)) { /* stopSlamModule() is under way: the ring is about to be released */
+  if (atomic_load(&G.stop_req) || !G.ring) { /* stopSlamModule() is under way or done: the ring is (about to be) released */
     pthread_mutex_unlock(&G.mu);
     return 0;
   }
-  if (!G.lossless && (G.count > QUEUE_HIGH_WATER || G.count + G.busy >= G.qcap)) {
-    /* SLAM.cpp:163-167: more than 10 waiting -> drop the oldest down to 5 */
-    while (G.count > QUEUE_LOW_WATER) {
-      G.head = (G.head + 1) % G.qcap;
-      G.count--;
-      G.dropped++;
+  if (!G.lossless && G.count > QUEUE_HIGH_WATER) {
+    /* SLAM.cpp:163-167: more than 10 waiting -> drop the oldest down to 5.  The survivors move down to the
+     * head of the queue (they are the newest 5, six or more slots further on, so source and destination never
+     * overlap): the ring keeps the shape [in flight][waiting][free] and the slot written below can never be one
+     * the tracker is still reading -- skipping over the dropped slots instead would let the write position
+     * run round into them when the tracker is slower than the producer. */
+    const int drop = G.count - QUEUE_LOW_WATER;
+    for (int k = 0; k < QUEUE_LOW_WATER; ++k) {
+      const int from = (G.head + drop + k) % G.qcap, to = (G.head + k) % G.qcap;
+      memcpy(G.ring + frame_px() * (size_t)to, G.ring + frame_px() * (size_t)from, frame_px() * sizeof(uint16_t));
+      G.ts[to] = G.ts[from];
     }
+    G.count = QUEUE_LOW_WATER;
+    G.dropped += drop;
   }
+  /* count <= 11 and at most two runs of `batch` frames in flight: count + busy < qcap, the slot is free */
   const int slot = (G.head + G.count) % G.qcap;
   /* reference depth is int16_t; values >= 32768 are reinterpreted as uint16 like the
    * CV_16UC1 view at SLAM.cpp:133 and then rejected by the depth_max gate */
@@ -311,6 +325,14 @@ void youthSlamSetOptions(int lossless, int batch) {
   if (batch >= 1) G.batch = batch > 64 ? 64 : batch;
 }
 
+/* The tracker handle is used by the worker thread; other threads touch it only while the worker has nothing
+ * queued or in flight, and hold the mutex meanwhile so that it cannot claim new frames (a producer waits in
+ * processSlamFrame for that long). */
+static void lock_idle(void) {
+  pthread_mutex_lock(&G.mu);
+  while (G.count > 0 || G.busy > 0) pthread_cond_wait(&G.idle, &G.mu);
+}
+
 /* wait until every accepted frame has been tracked */
 void youthSlamDrain(void) {
   if (!atomic_load(&G.running)) return;
@@ -324,13 +346,12 @@ void youthSlamDrain(void) {
  * through processSlamFrame() before this call are tracked first, so the order of the recording is kept. */
 int youthSlamProcessPackedFrames(const uint8_t* streams, const uint64_t* offsets, int n, int width, int height,
                                  const uint32_t* timestamps) {
-  if (!atomic_load(&G.running) || !G.h || !streams || !offsets || n < 1) return 0;
+  if (!atomic_load(&G.running) || !streams || !offsets || n < 1) return 0;
   if (width != G.cfg.width || height != G.cfg.height) return 0;
   float* poses = (float*)malloc(sizeof(float) * 12 * (size_t)G.batch);
   if (!poses) return 0;
-  pthread_mutex_lock(&G.mu);
-  while (G.count > 0 || G.busy > 0) pthread_cond_wait(&G.idle, &G.mu); /* the worker is idle: the handle is ours */
-  int ok = 1;
+  lock_idle(); /* the worker is idle: the handle is ours */
+  int ok = G.h != NULL;
   for (int f0 = 0; f0 < n && ok; f0 += G.batch) {
     const int cn = n - f0 < G.batch ? n - f0 : G.batch;
     const uint8_t* sp[1] = {streams};
@@ -360,8 +381,10 @@ int youthSlamProcessPackedFrames(const uint8_t* streams, const uint64_t* offsets
 }
 
 int youthSlamGetTrajectory(float* poses_out, uint32_t* timestamps_out, uint32_t* status_out, int max_frames) {
-  if (!atomic_load(&G.running) || !G.h) return 0;
-  int n = youth_cuda_get_trajectory(G.h, 0, 0, max_frames, poses_out, timestamps_out, status_out);
+  if (!atomic_load(&G.running)) return 0;
+  lock_idle();
+  int n = G.h ? youth_cuda_get_trajectory(G.h, 0, 0, max_frames, poses_out, timestamps_out, status_out) : 0;
+  pthread_mutex_unlock(&G.mu);
   return n < 0 ? 0 : n;
 }
 
@@ -374,20 +397,22 @@ void youthSlamStats(long* accepted, long* dropped, long* tracked) {
 }
 
 int saveSlamMap(const char* map_file) {
-  if (!atomic_load(&G.running) || !G.h || !map_file) {
+  if (!atomic_load(&G.running) || !map_file) {
     fprintf(stderr, "AlgorithmModule: not running\n");
     return 0;
   }
-  youthSlamDrain();
-  const int n = youth_cuda_frame_count(G.h, 0);
+  lock_idle(); /* every accepted frame is in the trajectory, and the handle is ours while we copy it out */
+  const int n = G.h ? youth_cuda_frame_count(G.h, 0) : -1;
   float* poses = (float*)malloc(sizeof(float) * 12 * (size_t)(n > 0 ? n : 1));
   uint32_t* ts = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(n > 0 ? n : 1));
-  if (!poses || !ts) {
+  if (n < 0 || !poses || !ts) {
+    pthread_mutex_unlock(&G.mu);
     free(poses);
     free(ts);
     return 0;
   }
   int got = youth_cuda_get_trajectory(G.h, 0, 0, n, poses, ts, NULL);
+  pthread_mutex_unlock(&G.mu);
   if (got < 0) got = 0;
   char path[1024];
   snprintf(path, sizeof(path), "%s_trajectory.txt", map_file);
@@ -421,13 +446,12 @@ int saveSlamMap(const char* map_file) {
 int isSlamModuleRunning(void) { return atomic_load(&G.running) ? 1 : 0; }
 
 int getSlamMapPoints(void) {
-  if (!atomic_load(&G.running) || !G.h) return 0;
-  if (youth_cuda_model_enabled(G.h)) {
+  if (!atomic_load(&G.running)) return 0;
+  if (atomic_load(&G.model_on)) {
     /* frame-to-model: the map has a size of its own -- the voxels the fused surface passes through
      * (GetAllMapPoints().size(), SLAM.cpp:212-217) */
-    pthread_mutex_lock(&G.mu);
-    while (G.count > 0 || G.busy > 0) pthread_cond_wait(&G.idle, &G.mu); /* the worker is idle: the handle is ours */
-    const long long n = youth_cuda_model_surface_voxels(G.h, 0);
+    lock_idle(); /* the worker is idle: the handle is ours */
+    const long long n = G.h ? youth_cuda_model_surface_voxels(G.h, 0) : 0;
     pthread_mutex_unlock(&G.mu);
     return n < 0 ? 0 : (n > 2147483647LL ? 2147483647 : (int)n);
   }
@@ -435,8 +459,9 @@ int getSlamMapPoints(void) {
 }
 
 void resetSlam(void) {
-  if (!atomic_load(&G.running) || !G.h) return;
-  youthSlamDrain();
-  youth_cuda_reset(G.h, -1);
+  if (!atomic_load(&G.running)) return;
+  lock_idle();
+  if (G.h) youth_cuda_reset(G.h, -1);
   atomic_store(&G.last_inliers, 0);
+  pthread_mutex_unlock(&G.mu);
 }

@@ -35,8 +35,14 @@ struct youth_cuda_handle {
 };
 
 static youth_cuda_handle* g_last; /* for stub_* inspection from the tests */
+static long g_torn; /* frames whose first / last pixel changed while track_batch held them */
 
-const char* youth_cuda_last_error(void) { return "stub"; }
+static const char* g_err = "";
+const char* youth_cuda_last_error(void) { return g_err; }
+static int fail(const char* why) {
+  g_err = why;
+  return 0;
+}
 int youth_cuda_abi_version(void) { return YOUTH_CUDA_ABI_VERSION; }
 
 int youth_cuda_default_config(youth_cuda_config* c) {
@@ -91,8 +97,8 @@ void youth_cuda_destroy(youth_cuda_handle* h) {
 int youth_cuda_track_batch(youth_cuda_handle* h, const uint16_t* const* depth, int n_frames, int mem_kind,
                            const uint32_t* timestamps_ms, float* poses_out) {
   (void)mem_kind;
-  if (!h || !depth || !depth[0] || n_frames < 1 || n_frames > h->cfg.batch) return 0;
-  if (h->count + n_frames > h->cfg.traj_capacity) return 0;
+  if (!h || !depth || !depth[0] || n_frames < 1 || n_frames > h->cfg.batch) return fail("stub: bad track_batch arguments");
+  if (h->count + n_frames > h->cfg.traj_capacity) return fail("stub: trajectory capacity exceeded");
   const size_t npx = (size_t)h->cfg.width * h->cfg.height;
   for (int i = 0; i < n_frames; ++i) {
     float* p = h->poses + 12 * (size_t)(h->count + i);
@@ -104,6 +110,12 @@ int youth_cuda_track_batch(youth_cuda_handle* h, const uint16_t* const* depth, i
     h->ts[h->count + i] = timestamps_ms ? timestamps_ms[i] : 0u;
   }
   if (h->delay_us > 0) usleep((useconds_t)h->delay_us * (useconds_t)n_frames);
+  /* the frames belong to the tracker until the call returns (the H2D copy of the real library reads them
+   * asynchronously): nobody may have written to them meanwhile */
+  for (int i = 0; i < n_frames; ++i) {
+    const float* p = h->poses + 12 * (size_t)(h->count + i);
+    if ((float)depth[0][npx * (size_t)i] != p[3] || depth[0][npx * (size_t)i + npx - 1] != depth[0][npx * (size_t)i]) ++g_torn;
+  }
   if (poses_out) memcpy(poses_out, h->poses + 12 * (size_t)h->count, sizeof(float) * 12 * (size_t)n_frames);
   h->count += n_frames;
   h->calls++;
@@ -176,3 +188,4 @@ long long youth_cuda_model_surface_voxels(youth_cuda_handle* h, int stream) {
 
 /* inspection for the tests */
 int stub_track_calls(void) { return g_last ? g_last->calls : -1; }
+long stub_torn_frames(void) { return g_torn; }

@@ -41,6 +41,7 @@ def fut(tmp_path_factory):
     L.algorithmModule.restype = C.c_void_p
     L.youth_bin_write_frame.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.youth_bin_write_eof.argtypes = [C.c_void_p]
+    L.stub_torn_frames.restype = C.c_long
     cfg = tmp_path_factory.mktemp("cfg") / "cam.yaml"
     cfg.write_text(f"%YAML:1.0\nCamera.width: {W}\nCamera.height: {H}\nCamera.fx: 57.03\nCamera.fy: 57.03\n"
                    "Camera.cx: 32.0\nCamera.cy: 24.0\nDepthMapFactor: 1000.0\n")
@@ -51,7 +52,7 @@ def fut(tmp_path_factory):
 
 def frame(marker):
     f = np.full((H, W), 1500, dtype=np.uint16)
-    f[0, 0] = marker
+    f[0, 0] = f[-1, -1] = marker  # the test double checks that both stay put while it holds the frame
     return f
 
 
@@ -96,7 +97,7 @@ def test_lossless_mode_tracks_every_frame_once_and_in_order(fut, tmp_path):
     n = 150
     buf = frame(0)
     for i in range(1, n + 1):
-        buf[0, 0] = i  # the caller's buffer is reused at once: the callee copies before returning (SLAM.cpp:133-134)
+        buf[0, 0] = buf[-1, -1] = i  # the caller's buffer is reused at once: the callee copies before returning (SLAM.cpp:133-134)
         assert fut.processSlamFrame(buf.ctypes.data, None, W, H, 33 * i) == 1
     assert fut.processSlamFrame(buf.ctypes.data, None, W + 8, H, 0) == 0  # not the configured size
     assert fut.processSlamFrame(None, None, W, H, 0) == 0
@@ -142,6 +143,9 @@ def test_default_back_pressure_drops_the_oldest_frames(fut, monkeypatch):
     assert len(marks) == tracked and marks == sorted(marks) and len(set(marks)) == len(marks)
     assert marks[-1] == n  # the newest frame always survives
     assert list(ts) == [int(m) for m in marks]
+    # no slot was written while the tracker held it (the write position must not run round into the frames in
+    # flight when frames are dropped faster than they are tracked)
+    assert fut.stub_torn_frames() == 0
     fut.stopSlamModule()
 
 
@@ -166,6 +170,7 @@ def test_stop_while_a_producer_is_pushing(fut, monkeypatch):
         th.join(timeout=10)
         assert not th.is_alive() and pushed and pushed[0] > 0
         assert fut.isSlamModuleRunning() == 0
+        assert fut.stub_torn_frames() == 0
 
 
 def write_recording(fut, path, n, t0=1000):
@@ -227,3 +232,26 @@ def test_algorithm_module_in_the_viewers_seat_follows_reference_playback(fut, tm
     rows = np.loadtxt(prefix + "_trajectory.txt")
     assert rows.shape == (n, 8)
     assert np.allclose(rows[:, 1], np.arange(1, n + 1)) and np.allclose(rows[:, 0], (5000 + 33 * np.arange(n)) / 1000.0)
+
+
+@pytest.mark.parametrize("sanitizer", ["thread", "address,undefined"])
+def test_facade_under_sanitizers(fut, tmp_path, sanitizer):
+    """Race / memory check of the facade's locking (the reference's plain-bool flags and
+    unguarded queue are racy, SLAM.cpp:17,29): tests/stub/facade_race_driver.c pushes frames from one thread, polls
+    status from another and drains / resets / saves / stops from a third, in both queue modes, built with
+    -fsanitize=thread and -fsanitize=address,undefined.  Any report fails the test."""
+    probe = tmp_path / "probe.c"
+    probe.write_text("int main(void){return 0;}\n")
+    flags = ["-fsanitize=" + sanitizer, "-g", "-O1", "-std=gnu11"]
+    ok = subprocess.run(["gcc", *flags, "-o", str(tmp_path / "probe"), str(probe)], capture_output=True).returncode == 0
+    if not ok or subprocess.run([str(tmp_path / "probe")], capture_output=True).returncode != 0:
+        pytest.skip(f"-fsanitize={sanitizer} does not run here")
+    src = [os.path.join(ROOT, "tests", "stub", f) for f in ("facade_race_driver.c", "youth_cuda_stub.c")] + \
+          [os.path.join(ROOT, "slam-rgbd_b200", "host", f) for f in HOST_SRC if f != "algorithm_module.c"]
+    exe = str(tmp_path / "driver")
+    res = subprocess.run(["gcc", *flags, "-I" + os.path.join(ROOT, "include"), "-o", exe, *src, "-lpthread", "-lrt", "-lm"],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([exe, fut.cfg_path.decode(), str(tmp_path / "out")], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0 and run.stdout.strip() == "ok", run.stderr[-3000:]
+    assert "Sanitizer" not in run.stderr and "runtime error" not in run.stderr, run.stderr[-3000:]
