@@ -97,6 +97,66 @@ def test_depth_gate_and_bilateral_properties(oracle):
     assert np.array_equal(d0, noisy.astype(np.float32))
 
 
+def _rn32(x):
+    """a Fraction rounded to the nearest float32, ties to even, in exact arithmetic (no double rounding)"""
+    from fractions import Fraction
+
+    if x == 0:
+        return np.float32(0.0)
+    sign, a = (-1 if x < 0 else 1), abs(x)
+    e = a.numerator.bit_length() - a.denominator.bit_length() - 24
+    while a / Fraction(2) ** e >= 1 << 24:
+        e += 1
+    while e > -149 and a / Fraction(2) ** e < 1 << 23:
+        e -= 1
+    e = max(e, -149)  # subnormals: multiples of 2^-149
+    return np.float32(sign * float(round(a / Fraction(2) ** e) * Fraction(2) ** e))  # round(): half to even; exact in double
+
+
+def test_bilateral_against_exact_rational_restatement(oracle):
+    """Stage 1 restated independently of the C oracle, tap by tap in exact rational arithmetic with one explicit
+    float32 rounding per written operation (product of the two table weights, running weight sum, FUSED
+    multiply-add of the numerator, final division) -- pure Python, so a small frame:
+    holes, values outside the depth gate, a step beyond 3 sigma_r and all four borders are in it.  Bit-equal."""
+    from fractions import Fraction as Fr
+
+    w, h = 24, 16
+    cfg = small_cfg(oracle, w=w, h=h, depth_min_mm=400, depth_max_mm=5000)
+    rng = np.random.default_rng(11)
+    raw = (1500 + rng.integers(-25, 26, size=(h, w))).astype(np.uint16)
+    raw[:, 14:] += 400                      # a step far beyond the 90 mm range cut
+    raw[rng.random((h, w)) < 0.06] = 0      # holes
+    raw[3, 5], raw[9, 20] = 300, 6000       # outside the depth gate
+    got = np.empty((h, w), dtype=np.float32)
+    oracle.lib().yo_bilateral(C.byref(cfg), raw.ctypes.data, got.ctypes.data)
+    ss, sr = float(cfg.sigma_space_px), float(cfg.sigma_range_mm)
+    cut = int(np.float32(3.0) * np.float32(sr))
+    ws = [[np.float32(np.exp(-float(dx * dx + dy * dy) / (2.0 * ss * ss))) for dx in range(-3, 4)] for dy in range(-3, 4)]
+    wr = [np.float32(np.exp(-float(i) * float(i) / (2.0 * sr * sr))) for i in range(cut + 1)]
+    valid = lambda d: 400 <= d <= 5000
+    want = np.zeros((h, w), dtype=np.float32)
+    for y in range(h):
+        for x in range(w):
+            dc = int(raw[y, x])
+            if not valid(dc):
+                continue
+            sw, swd = np.float32(0), np.float32(0)
+            for dy in range(-3, 4):
+                for dx in range(-3, 4):
+                    yy, xx = y + dy, x + dx
+                    if not (0 <= yy < h and 0 <= xx < w):
+                        continue
+                    dk = int(raw[yy, xx])
+                    if not valid(dk) or abs(dk - dc) > cut:
+                        continue
+                    wgt = _rn32(Fr(float(ws[dy + 3][dx + 3])) * Fr(float(wr[abs(dk - dc)])))
+                    sw = _rn32(Fr(float(sw)) + Fr(float(wgt)))
+                    swd = _rn32(Fr(float(wgt)) * dk + Fr(float(swd)))  # fma: one rounding
+            want[y, x] = _rn32(Fr(float(swd)) / Fr(float(sw)))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert (got > 0).sum() > 300 and np.abs(got[got > 0] - raw[got > 0]).max() > 1.0  # it did filter
+
+
 def test_pyrdown_rule(oracle):
     cfg = small_cfg(oracle)
     src = np.zeros((4, 8), dtype=np.float32)
@@ -181,6 +241,110 @@ def test_reduction_matches_float64_sum(oracle, small_seq):
         s2, c2 = oracle.icp_sums(cfg2, 0, cur, prev, pose)
         assert np.array_equal(c2, corr) and s2[31] == sums[31]
         assert np.allclose(s2[:31], sums[:31], rtol=1e-4, atol=1e-4)
+
+
+def test_association_and_reduction_against_exact_rational_restatement(oracle, pkg):
+    """Stages 3 + 4 restated independently of the C oracle: per pixel the nested-fma
+    transform, the reciprocal and projection fma, the gates in their order with their reject codes, residual and
+    Jacobian as fma chains, the 32 fused accumulations; then the lane / run / chain reduction order.  Exact rational
+    arithmetic with one explicit float32 (or, across runs, float64) rounding per written operation.  The
+    correspondence image must be equal and the 32 sums bit-equal."""
+    from fractions import Fraction as Fr
+
+    w, h, ppt = 64, 48, 4
+    cfg = small_cfg(oracle, w=w, h=h, levels=1, icp_ppt=ppt)
+    cfg.iters[0] = 1
+    raw = pkg.synth_sequence(2, w, h, sequence=3)
+    prev, cur = oracle.OFrame(cfg, raw[0]), oracle.OFrame(cfg, raw[1])
+    rot = Rotation.from_rotvec([0.004, -0.007, 0.003]).as_matrix()
+    pose = np.concatenate([rot, [[0.006], [-0.004], [0.009]]], axis=1).astype(np.float32).reshape(12)
+    sums, corr = oracle.icp_sums(cfg, 0, cur, prev, pose)
+
+    F = lambda v: Fr(float(v))
+    mul = lambda a, b: _rn32(F(a) * F(b))
+    sub = lambda a, b: _rn32(F(a) - F(b))
+    add = lambda a, b: _rn32(F(a) + F(b))
+    fma = lambda a, b, c: _rn32(F(a) * F(b) + F(c))
+    f32 = np.float32
+    g = oracle.level_geometry(cfg, 0)
+    fx, fy, cxh, cyh = f32(g.fx), f32(g.fy), add(f32(g.cx), f32(0.5)), add(f32(g.cy), f32(0.5))
+    dist2_thr, cos_thr = mul(f32(cfg.dist_thresh_m), f32(cfg.dist_thresh_m)), f32(cfg.cos_thresh)
+    P = [f32(v) for v in pose]
+    vc, nc = cur.vmap(0).reshape(-1, 4), cur.nmap(0).reshape(-1, 4)
+    vp, npv = prev.vmap(0).reshape(-1, 4), prev.nmap(0).reshape(-1, 4)
+    PA = [0, 0, 0, 1, 1, 1, 2, 2, 3, 3, 4, 5, 6, 6, 6]
+    PB = [0, 2, 4, 0, 2, 4, 2, 4, 2, 4, 4, 4, 0, 2, 4]
+    FLT_MIN = f32(1.17549435e-38)
+
+    def pixel(p, acc):
+        if vc[p, 3] == 0 or nc[p, 3] == 0:
+            return -1
+        x, y, z = vc[p, 0], vc[p, 1], vc[p, 2]
+        tx = fma(P[0], x, fma(P[1], y, fma(P[2], z, P[3])))
+        ty = fma(P[4], x, fma(P[5], y, fma(P[6], z, P[7])))
+        tz = fma(P[8], x, fma(P[9], y, fma(P[10], z, P[11])))
+        if not tz >= FLT_MIN:
+            return -2
+        iz = _rn32(1 / F(tz))
+        ur, vr = fma(mul(tx, fx), iz, cxh), fma(mul(ty, fy), iz, cyh)
+        if not (0 <= ur < w and 0 <= vr < h):
+            return -3
+        q = int(vr) * w + int(ur)
+        if vp[q, 3] == 0 or npv[q, 3] == 0:
+            return -4
+        dx, dy, dz = sub(vp[q, 0], tx), sub(vp[q, 1], ty), sub(vp[q, 2], tz)
+        if not fma(dz, dz, fma(dy, dy, mul(dx, dx))) <= dist2_thr:
+            return -5
+        nx, ny, nz = nc[p, 0], nc[p, 1], nc[p, 2]
+        rnx = fma(P[2], nz, fma(P[1], ny, mul(P[0], nx)))
+        rny = fma(P[6], nz, fma(P[5], ny, mul(P[4], nx)))
+        rnz = fma(P[10], nz, fma(P[9], ny, mul(P[8], nx)))
+        n0, n1, n2 = npv[q, 0], npv[q, 1], npv[q, 2]
+        if not fma(rnz, n2, fma(rny, n1, mul(rnx, n0))) >= cos_thr:
+            return -6
+        X = [fma(ty, n2, -mul(tz, n1)), fma(tz, n0, -mul(tx, n2)), fma(tx, n1, -mul(ty, n0)), n0, n1, n2,
+             fma(n2, dz, fma(n1, dy, mul(n0, dx))), f32(1.0)]
+        for k in range(15):
+            acc[2 * k] = fma(X[PA[k]], X[PB[k]], acc[2 * k])
+            acc[2 * k + 1] = fma(X[PA[k]], X[PB[k] + 1], acc[2 * k + 1])
+        acc[30] = fma(X[6], X[6], acc[30])
+        acc[31] = fma(X[7], X[7], acc[31])
+        return q
+
+    npix, lanes = w * h, 32
+    nruns = -(-npix // (lanes * ppt))
+    want_corr = np.empty(npix, dtype=np.int32)
+    partial = np.zeros((nruns, 32), dtype=np.float32)
+    for run in range(nruns):
+        acc = [[f32(0.0)] * 32 for _ in range(lanes)]
+        for j in range(ppt):
+            for l in range(lanes):
+                p = j * lanes * nruns + lanes * run + l
+                if p < npix:
+                    want_corr[p] = pixel(p, acc[l])
+        for k in range(32):
+            v = [acc[l][k] for l in range(lanes)]
+            s_ = 16
+            while s_ >= 1:
+                for l in range(s_):
+                    v[l] = add(v[l], v[l + s_])
+                s_ >>= 1
+            partial[run, k] = v[0]
+    want = np.zeros(32, dtype=np.float64)
+    for k in range(32):
+        chains = []
+        for c in range(8):
+            d = 0.0
+            for run in range(c, nruns, 8):
+                d = d + float(partial[run, k])  # IEEE double addition
+            chains.append(d)
+        tot = chains[0]
+        for c in range(1, 8):
+            tot = tot + chains[c]
+        want[k] = tot
+    assert np.array_equal(corr.reshape(-1), want_corr)
+    assert (want_corr >= 0).sum() > 1500 and len(set(want_corr[want_corr < 0])) >= 3  # matches and several reject kinds
+    assert np.array_equal(sums.view(np.uint64), want.view(np.uint64))
 
 
 def test_solve_update_against_numpy_scipy(oracle):
