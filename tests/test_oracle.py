@@ -243,6 +243,85 @@ def test_reduction_matches_float64_sum(oracle, small_seq):
         assert np.allclose(s2[:31], sums[:31], rtol=1e-4, atol=1e-4)
 
 
+def _sqrt32(x):
+    """correctly rounded float32 square root of a positive float32, through an integer square root"""
+    import math
+    from fractions import Fraction
+
+    q = Fraction(float(x)) * Fraction(4) ** 80  # sqrt(q) = sqrt(x) * 2^80, far more than 24 significant bits
+    r = math.isqrt(q.numerator // q.denominator)
+    exact = q.denominator == 1 and r * r == q.numerator
+    proxy = Fraction(r) if exact else Fraction(2 * r + 1, 2)  # strictly inside (r, r+1): never a float32 tie
+    return _rn32(proxy / Fraction(2) ** 80)
+
+
+def test_pyramid_vertices_normals_against_exact_rational_restatement(oracle, pkg):
+    """Stages 1b + 2 restated independently of the C oracle: 2x2 pyramid rule with
+    its sample counts, back-projection (viewerModule.c:343-345) with the per-level intrinsics, cross-product normals
+    with the correctly rounded square root and reciprocal -- every operation rounded once, none fused.  Bit-equal at
+    all three levels, validity included."""
+    from fractions import Fraction as Fr
+
+    w, h = 64, 48
+    cfg = small_cfg(oracle, w=w, h=h)
+    raw = pkg.synth_sequence(1, w, h, sequence=5, noise=1)[0]
+    fr = oracle.OFrame(cfg, raw)
+    F = lambda v: Fr(float(v))
+    mul = lambda a, b: _rn32(F(a) * F(b))
+    sub = lambda a, b: _rn32(F(a) - F(b))
+    add = lambda a, b: _rn32(F(a) + F(b))
+    div = lambda a, b: _rn32(F(a) / F(b))
+    f32 = np.float32
+    thr = mul(f32(3.0), f32(cfg.sigma_range_mm))
+    depth = [fr.depth(0).copy()]
+    for level in range(1, 3):
+        src = depth[-1]
+        hh, ww = src.shape[0] // 2, src.shape[1] // 2
+        dst, cnt = np.zeros((hh, ww), dtype=np.float32), np.zeros((hh, ww), dtype=np.uint8)
+        for y in range(hh):
+            for x in range(ww):
+                smp = [src[2 * y, 2 * x], src[2 * y, 2 * x + 1], src[2 * y + 1, 2 * x], src[2 * y + 1, 2 * x + 1]]
+                centre = next((v for v in smp if v > 0), None)
+                if centre is None:
+                    continue
+                tot, n = f32(0.0), 0
+                for v in smp:
+                    if v > 0 and abs(sub(v, centre)) <= thr:
+                        tot, n = add(tot, v), n + 1
+                dst[y, x], cnt[y, x] = div(tot, f32(n)), n
+        assert np.array_equal(fr.depth(level).view(np.uint32), dst.view(np.uint32))
+        assert np.array_equal(fr.pyrcnt(level), cnt) and cnt.max() == 4
+        depth.append(dst)
+    factor = f32(cfg.depth_factor)
+    for level in range(3):
+        g = oracle.level_geometry(cfg, level)
+        d = depth[level]
+        hh, ww = d.shape
+        V = np.zeros((hh, ww, 4), dtype=np.float32)
+        for v in range(hh):
+            for u in range(ww):
+                if d[v, u] > 0:
+                    z = div(d[v, u], factor)
+                    V[v, u] = (div(mul(sub(f32(u), f32(g.cx)), z), f32(g.fx)), div(mul(sub(f32(v), f32(g.cy)), z), f32(g.fy)), z, 1.0)
+        N = np.zeros((hh, ww, 4), dtype=np.float32)
+        for v in range(hh - 1):
+            for u in range(ww - 1):
+                p, px, py = V[v, u], V[v, u + 1], V[v + 1, u]
+                if p[3] == 0 or px[3] == 0 or py[3] == 0:
+                    continue
+                ax, ay, az = sub(px[0], p[0]), sub(px[1], p[1]), sub(px[2], p[2])
+                bx, by, bz = sub(py[0], p[0]), sub(py[1], p[1]), sub(py[2], p[2])
+                nx, ny, nz = sub(mul(ay, bz), mul(az, by)), sub(mul(az, bx), mul(ax, bz)), sub(mul(ax, by), mul(ay, bx))
+                len2 = add(add(mul(nx, nx), mul(ny, ny)), mul(nz, nz))
+                if not len2 > f32(1e-24):
+                    continue
+                inv = div(f32(1.0), _sqrt32(len2))
+                N[v, u] = (mul(nx, inv), mul(ny, inv), mul(nz, inv), 1.0)
+        assert np.array_equal(fr.vmap(level).view(np.uint32), V.view(np.uint32)), level
+        assert np.array_equal(fr.nmap(level).view(np.uint32), N.view(np.uint32)), level
+        assert N[..., 3].sum() > 0.5 * hh * ww
+
+
 def test_association_and_reduction_against_exact_rational_restatement(oracle, pkg):
     """Stages 3 + 4 restated independently of the C oracle: per pixel the nested-fma
     transform, the reciprocal and projection fma, the gates in their order with their reject codes, residual and
@@ -375,6 +454,89 @@ def test_solve_update_against_numpy_scipy(oracle):
         want = np.concatenate([Rinc @ R0, (Rinc @ t0 + V @ u)[:, None]], axis=1).reshape(12)
         assert np.allclose(pose_d, want, rtol=0, atol=1e-9)
         assert np.array_equal(pose_f, pose_d.astype(np.float32))
+
+
+def test_solve_and_pose_update_against_operation_by_operation_restatement(oracle):
+    """Stage 5 restated independently of the C oracle in Python floats -- IEEE doubles,
+    one rounding per written operation, correctly rounded sqrt, no fused operations: Cholesky with one reciprocal
+    per column, ascending forward and DESCENDING back substitution, the three 12-term Horner series in theta^2, the
+    SE(3) exponential and T <- exp(xi) T with the parenthesisation of the specification.  Bit-equal, small and large
+    rotations."""
+    import math
+
+    rng = np.random.default_rng(9)
+    cfg = oracle.default_config()
+    fact = [float(math.factorial(n)) for n in range(28)]
+
+    def mat3(a, b):
+        return [(a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j]) + a[3 * i + 2] * b[6 + j] for i in range(3) for j in range(3)]
+
+    def solve_update(sums, pose):
+        A = [[float(sums[SLOT_A[i][j]]) for j in range(6)] for i in range(6)]
+        b = [float(sums[24 + i]) for i in range(6)]
+        scale = max(A[i][i] for i in range(6))
+        L = [[0.0] * 6 for _ in range(6)]
+        inv = [0.0] * 6
+        for j in range(6):
+            d = A[j][j]
+            for m in range(j):
+                d = d - L[j][m] * L[j][m]
+            assert d > 1e-12 * scale
+            L[j][j] = math.sqrt(d)
+            inv[j] = 1.0 / L[j][j]
+            for i in range(j + 1, 6):
+                s_ = A[i][j]
+                for m in range(j):
+                    s_ = s_ - L[i][m] * L[j][m]
+                L[i][j] = s_ * inv[j]
+        y, x = [0.0] * 6, [0.0] * 6
+        for i in range(6):
+            s_ = b[i]
+            for m in range(i):
+                s_ = s_ - L[i][m] * y[m]
+            y[i] = s_ * inv[i]
+        for i in range(5, -1, -1):
+            s_ = y[i]
+            for m in range(5, i, -1):
+                s_ = s_ - L[m][i] * x[m]
+            x[i] = s_ * inv[i]
+        wx, wy, wz = x[0], x[1], x[2]
+        t2 = (wx * wx + wy * wy) + wz * wz
+        a = bb = c = 0.0
+        for k in range(11, -1, -1):
+            sgn = -1.0 if k & 1 else 1.0
+            a = a * t2 + sgn / fact[2 * k + 1]
+            bb = bb * t2 + sgn / fact[2 * k + 2]
+            c = c * t2 + sgn / fact[2 * k + 3]
+        W = [0.0, -wz, wy, wz, 0.0, -wx, -wy, wx, 0.0]
+        W2 = mat3(W, W)
+        ident = [1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0]
+        Ri = [(ident[i] + a * W[i]) + bb * W2[i] for i in range(9)]
+        V = [(ident[i] + bb * W[i]) + c * W2[i] for i in range(9)]
+        ti = [(V[3 * i] * x[3] + V[3 * i + 1] * x[4]) + V[3 * i + 2] * x[5] for i in range(3)]
+        R = [float(pose[4 * i + j]) for i in range(3) for j in range(3)]
+        t = [float(pose[4 * i + 3]) for i in range(3)]
+        Rn = mat3(Ri, R)
+        tn = [((Ri[3 * i] * t[0] + Ri[3 * i + 1] * t[1]) + Ri[3 * i + 2] * t[2]) + ti[i] for i in range(3)]
+        return np.array([[Rn[3 * i], Rn[3 * i + 1], Rn[3 * i + 2], tn[i]] for i in range(3)]).reshape(12)
+
+    for trial in range(30):
+        J = rng.normal(size=(300, 6))
+        xi = rng.normal(size=6) * (0.01 if trial < 20 else 1.5)
+        A, b = J.T @ J, J.T @ (J @ xi)
+        sums = np.zeros(32)
+        for i in range(6):
+            for j in range(i, 6):
+                sums[SLOT_A[i][j]] = A[i, j]
+        sums[24:30] = b
+        sums[31] = 300
+        R0 = Rotation.from_rotvec(rng.normal(size=3) * 0.4).as_matrix()
+        pose_d = np.concatenate([R0, rng.normal(size=(3, 1))], axis=1).reshape(12).copy()
+        want = solve_update(sums, pose_d)
+        pose_f = np.zeros(12, dtype=np.float32)
+        assert oracle.lib().yo_solve_update(C.byref(cfg), sums.ctypes.data, pose_d.ctypes.data, pose_f.ctypes.data) == 1
+        assert np.array_equal(pose_d.view(np.uint64), want.view(np.uint64)), trial
+        assert np.array_equal(pose_f, want.astype(np.float32))
 
 
 def test_solve_failure_policy(oracle):
