@@ -32,21 +32,33 @@ static int cmd_gen(int argc, char** argv) {
   const int w = argc > 6 ? atoi(argv[5]) : 640, h = argc > 6 ? atoi(argv[6]) : 480;
   youth_synth_config sc;
   youth_synth_default(&sc, w, h, seq);
+  if (n < 1 || w < 1 || h < 1) return 2;
   FILE* f = fopen(path, "wb");
   if (!f) return 1;
   uint16_t* d = (uint16_t*)malloc((size_t)w * h * 2);
   float* gt = (float*)malloc(sizeof(float) * 12 * (size_t)n);
   uint32_t* ts = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)n);
-  for (int i = 0; i < n; ++i) {
+  int failed = !d || !gt || !ts;
+  for (int i = 0; i < n && !failed; ++i) {
     youth_synth_frame(&sc, i, d);
     ts[i] = (uint32_t)(33 * i);
-    if (!youth_bin_write_frame(f, (uint32_t)i, ts[i], w, h, d, NULL)) return 1;
+    if (!youth_bin_write_frame(f, (uint32_t)i, ts[i], w, h, d, NULL)) {
+      failed = 1;
+      break;
+    }
     double G[12];
     youth_synth_gt(&sc, i, G);
     for (int k = 0; k < 12; ++k) gt[12 * i + k] = (float)G[k];
   }
-  youth_bin_write_eof(f);
+  if (!failed) youth_bin_write_eof(f);
   fclose(f);
+  if (failed) {
+    fprintf(stderr, "gen: cannot write %s\n", path);
+    free(d);
+    free(gt);
+    free(ts);
+    return 1;
+  }
   char gp[1024];
   snprintf(gp, sizeof(gp), "%s.gt.txt", path);
   youth_tum_write(gp, gt, ts, n);
@@ -77,6 +89,7 @@ static int cmd_pack(int argc, char** argv) {
   FILE* out = in ? fopen(argv[3], "wb") : NULL;
   if (!in || !out) {
     fprintf(stderr, "pack: cannot open files\n");
+    if (in) fclose(in);
     return 1;
   }
   enum { RUN = 32 };
@@ -114,11 +127,21 @@ static int cmd_pack(int argc, char** argv) {
         depth = (uint16_t*)malloc(fpx * 2 * RUN);
         color = (uint8_t*)malloc(fpx * 3 * RUN);
         packed = (uint8_t*)malloc(max_b * RUN);
+        if (!depth || !color || !packed) {
+          fprintf(stderr, "pack: out of memory\n");
+          rc = 1;
+          break;
+        }
       } else if (fpx != (size_t)h.width * h.height) {
         rc = 1;
         break;
       }
       (void)pos;
+      if (h.depthDataSize != fpx * 2) { /* raw 16-bit records only (an already packed recording has nothing to gain) */
+        fprintf(stderr, "pack: record %u is not a raw depth frame (%u payload bytes)\n", h.frameId, h.depthDataSize);
+        rc = 1;
+        break;
+      }
       if (fread(depth + fpx * n, 1, h.depthDataSize, in) != h.depthDataSize) { more = 0; break; }
       if (h.colorDataSize > fpx * 3 || fread(color + fpx * 3 * n, 1, h.colorDataSize, in) != h.colorDataSize) { more = 0; break; }
       hdr[n++] = h;
