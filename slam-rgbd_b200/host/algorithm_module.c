@@ -88,6 +88,11 @@ void* algorithmModule(void* id) {
       frames += nrun;
       nrun = 0;
     }
+    if ((size_t)hdr.depthDataSize != (size_t)hdr.width * hdr.height * 2) {
+      fprintf(stderr, "algorithmModule: record %u carries %u depth bytes for %ux%u, stopping\n", hdr.frameId,
+              hdr.depthDataSize, hdr.width, hdr.height);
+      break;
+    }
     if (!processSlamFrame((const int16_t*)depth, NULL, hdr.width, hdr.height, hdr.timestamp)) break;
     ++frames;
   }

@@ -197,6 +197,17 @@ def test_algorithm_module_replays_a_recording(fut, tmp_path, monkeypatch):
     assert np.allclose(rows[:, 1], np.arange(1, 41)) and np.allclose(rows[:, 0], (1000 + 33 * np.arange(40)) / 1000.0)
     fut.algorithmModule(b"/nonexistent/recording.bin")  # reported on stderr, module stopped again
     assert fut.isSlamModuleRunning() == 0
+    # a record whose depth payload is not a whole frame ends the replay (nothing is read past the payload)
+    import struct
+
+    bad = str(tmp_path / "bad.bin").encode()
+    write_recording(fut, bad, 3)
+    blob = open(bad, "rb").read()[:-28]  # without the end-of-file record
+    blob += struct.pack("<IIHHHxxIII", 3, 1099, 1, W, H, 100, 0, 0) + bytes(100)
+    blob += struct.pack("<IIHHHxxIII", 0, 0, 0xFF, 0, 0, 0, 0, 0)
+    open(bad, "wb").write(blob)
+    fut.algorithmModule(bad)
+    assert np.loadtxt(prefix + "_trajectory.txt").shape == (3, 8)
 
 
 def test_algorithm_module_in_the_viewers_seat_follows_reference_playback(fut, tmp_path, monkeypatch):
