@@ -35,18 +35,35 @@ int youth_config_from_yaml(const char* path, youth_cuda_config* cfg) {
   if (!f) return 0;
   char line[512];
   double v;
+  int ok = 1;
+  /* a value the tracker cannot mean anything by (not finite, beyond float / image-size range) makes the file
+   * invalid rather than being converted (out-of-range conversions are undefined behaviour in C) */
   while (fgets(line, sizeof(line), f)) {
     if (line[0] == '#' || line[0] == '%') continue;
-    if (parse_key(line, "Camera.fx", &v)) cfg->fx = (float)v;
-    else if (parse_key(line, "Camera.fy", &v)) cfg->fy = (float)v;
-    else if (parse_key(line, "Camera.cx", &v)) cfg->cx = (float)v;
-    else if (parse_key(line, "Camera.cy", &v)) cfg->cy = (float)v;
-    else if (parse_key(line, "Camera.width", &v)) cfg->width = (int32_t)v;
-    else if (parse_key(line, "Camera.height", &v)) cfg->height = (int32_t)v;
-    else if (parse_key(line, "DepthMapFactor", &v)) { if (v > 0) cfg->depth_factor = (float)v; }
+    float* fdst = NULL;
+    int32_t* idst = NULL;
+    if (parse_key(line, "Camera.fx", &v)) fdst = &cfg->fx;
+    else if (parse_key(line, "Camera.fy", &v)) fdst = &cfg->fy;
+    else if (parse_key(line, "Camera.cx", &v)) fdst = &cfg->cx;
+    else if (parse_key(line, "Camera.cy", &v)) fdst = &cfg->cy;
+    else if (parse_key(line, "Camera.width", &v)) idst = &cfg->width;
+    else if (parse_key(line, "Camera.height", &v)) idst = &cfg->height;
+    else if (parse_key(line, "DepthMapFactor", &v)) {
+      if (v >= 1e-30 && v < 1e30) cfg->depth_factor = (float)v; /* ORB-SLAM3 ignores a non-positive factor too */
+      else if (!(v <= 0)) ok = 0;
+      continue;
+    }
+    if (fdst) {
+      if (v > -1e30 && v < 1e30) *fdst = (float)v;
+      else ok = 0;
+    } else if (idst) {
+      if (v >= 1 && v <= 65535) *idst = (int32_t)v;
+      else ok = 0;
+    }
   }
   fclose(f);
-  return 1;
+  if (!ok) youth_cuda_default_config(cfg);
+  return ok;
 }
 
 void youth_pose_to_quat(const float P[12], double q[4]) {

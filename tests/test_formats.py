@@ -278,3 +278,29 @@ def test_pose_message_roundtrip(host):
     r = host.youth_reasm_create()
     assert host.youth_reasm_feed(r, msg.ctypes.data, n) == 0
     host.youth_reasm_destroy(r)
+
+
+def test_host_parsers_survive_fuzzed_input_under_sanitizers(tmp_path):
+    """tests/stub/host_fuzz_driver.c: mutated / truncated mq messages, recordings and camera YAML files against
+    youth_reasm_feed, youth_pose_msg_parse, youth_bin_read_frame and youth_config_from_yaml, built with
+    -fsanitize=address,undefined (+ float-cast-overflow).  They may reject, never misbehave."""
+    import subprocess
+
+    flags = ["-fsanitize=address,undefined", "-fsanitize=float-cast-overflow", "-fno-sanitize-recover=undefined", "-g", "-O1",
+             "-std=gnu11"]
+    probe = tmp_path / "probe.c"
+    probe.write_text("int main(void){return 0;}\n")
+    ok = subprocess.run(["gcc", *flags, "-o", str(tmp_path / "probe"), str(probe)], capture_output=True).returncode == 0
+    if not ok or subprocess.run([str(tmp_path / "probe")], capture_output=True).returncode != 0:
+        pytest.skip("sanitizer builds do not run here")
+    src = [os.path.join(ROOT, "tests", "stub", f) for f in ("host_fuzz_driver.c", "youth_cuda_stub.c")] + \
+          [os.path.join(ROOT, "slam-rgbd_b200", "host", f) for f in ("youth_frameio.c", "youth_config.c")]
+    exe = str(tmp_path / "fuzz")
+    res = subprocess.run(["gcc", *flags, "-I" + os.path.join(ROOT, "include"), "-o", exe, *src, "-lrt", "-lm"],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    scratch = tmp_path / "scratch"
+    scratch.mkdir()
+    run = subprocess.run([exe, str(scratch)], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0 and run.stdout.startswith("ok "), (run.stdout + run.stderr)[-3000:]
+    assert "runtime error" not in run.stderr and "Sanitizer" not in run.stderr, run.stderr[-3000:]
