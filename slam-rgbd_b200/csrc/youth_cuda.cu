@@ -700,6 +700,16 @@ static int enqueue_preprocess(youth_cuda_handle* h, const uint16_t* const* raw_d
       ip.r_fy[l] = h->r_fy[l];
     }
 #endif
+#if YK_FAST_DIV
+    if (h->fast_div) {
+      if (!c.bilateral)
+        k_ingest<YK_INGEST_RAW, true><<<grid, 256, 0, h->stream>>>(ip);
+      else if (h->range_cut + 2 <= YK_WT_STRIDE && !h->ingest_generic)
+        k_ingest<YK_INGEST_BILATERAL_WT, true><<<grid, 256, 0, h->stream>>>(ip);
+      else
+        k_ingest<YK_INGEST_BILATERAL, true><<<grid, 256, 0, h->stream>>>(ip);
+    } else
+#endif
     if (!c.bilateral)
       k_ingest<YK_INGEST_RAW><<<grid, 256, 0, h->stream>>>(ip);
     else if (h->range_cut + 2 <= YK_WT_STRIDE && !h->ingest_generic)
