@@ -164,3 +164,45 @@ def test_sensor_to_logging_to_algorithm_drop_in(pkg, small_seq, ref):
     want = direct.track_batch([frames])[0]
     direct.close()
     assert np.array_equal(poses.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("YOUTH_TEST_MQ_MODE") != "1",
+                    reason="opt-in until its first run on a GPU box (written after the round's last GPU minute): YOUTH_TEST_MQ_MODE=1")
+def test_playback_to_algorithm_module_on_the_viewer_queue(pkg, small_seq, ref, tmp_path):
+    """Recording -> the reference's own startPlayback / playbackThread -> /logger_viewer_queue ->
+    algorithmModule("mq:/logger_viewer_queue") -> tracker: the TUM trajectory equals direct tracking of the frames."""
+    import subprocess
+    import threading
+
+    frames, _ = small_seq
+    paths = pkg.lib_paths()
+    rec = str(tmp_path / "rec.bin")
+    assert subprocess.run([paths["harness"], "gen", rec, "6"], capture_output=True).returncode == 0  # sequence 0 = small_seq
+    host = pkg.host_lib()
+    prefix = str(tmp_path / "run")
+    os.environ["YOUTH_SLAM_OUT"] = prefix
+    os.environ["YOUTH_SLAM_MQ_IDLE_MS"] = "3000"
+    cb_run, cb_proc = RUNNING(lambda: 0), PROCESS(lambda *a: 1)
+    ref.ref_hook_install(C.cast(cb_run, C.c_void_p), C.cast(cb_proc, C.c_void_p))
+    assert ref.ref_pipeline_start() == 1
+    try:
+        ref.ref_viewer_stop()
+        host.youthSlamSetOptions(1, 4)
+        th = threading.Thread(target=lambda: host.algorithmModule(C.c_char_p(b"mq:/logger_viewer_queue")))
+        th.start()
+        assert wait_for(lambda: host.isSlamModuleRunning() == 1, timeout=120)  # first CUDA init on a fresh box is slow
+        assert ref.ref_start_playback(rec.encode()) == 1
+        th.join(timeout=120)
+        assert not th.is_alive()
+    finally:
+        ref.ref_pipeline_stop()
+        del os.environ["YOUTH_SLAM_OUT"], os.environ["YOUTH_SLAM_MQ_IDLE_MS"]
+    rows = np.loadtxt(prefix + "_trajectory.txt")
+    assert rows.shape == (6, 8)
+    from slam_rgbd_b200.binding import Tracker
+
+    direct = Tracker(pkg.default_config(batch=6))
+    want = direct.track_batch([frames])[0]
+    direct.close()
+    assert np.allclose(rows[:, 1:4], want[:, [3, 7, 11]], atol=1e-6)
