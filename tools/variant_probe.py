@@ -1,0 +1,104 @@
+#!/usr/bin/env python
+"""Quick A/B of A/B builds of libyouth_cuda.so (slam-rgbd_b200/lib/variants/, `make next-variants`) on a GPU box,
+without torch: for the default library and each variant, in its own process, track the same 300-frame synthetic
+sequence from page-locked host memory (one launch group, icp_ppt 128 = what bench.py runs), print the SHA-1 of the
+trajectory (bit-exactness against the default library is the gate) and the per-kernel-class CUDA-event times of
+profiled steps (youth_cuda_profile_*; A/B evidence, not a bench value).  One JSON line per library, flushed at once.
+    python tools/variant_probe.py [--frames 300] [--reps 5] [names ...]        (default: default xy3 xy1 xy2 fastdiv)
+"""
+import argparse
+import ctypes as C
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+SHM = "/dev/shm/youth_variant_probe_frames.npy"
+
+
+def child(name, frames_n, reps):
+    t0 = time.time()
+    import youth_pkg
+
+    pkg = youth_pkg.load()
+    from slam_rgbd_b200 import binding as B
+
+    frames = np.load(SHM, mmap_mode="r")
+    cfg = pkg.default_config(batch=frames_n, icp_ppt=128, traj_capacity=frames_n)
+    trk = B.Tracker(cfg)
+    lib = trk.lib
+    nbytes = frames_n * 480 * 640 * 2
+    pinned = lib.youth_cuda_host_alloc(nbytes)
+    assert pinned
+    C.memmove(pinned, frames.ctypes.data if hasattr(frames, "ctypes") else np.ascontiguousarray(frames).ctypes.data, nbytes)
+    t_init = time.time() - t0
+
+    def step():
+        trk.reset()
+        trk.track_batch_ptrs([pinned], frames_n, B.MEM_HOST_PINNED)
+        trk.sync()
+
+    for _ in range(2):
+        step()
+    poses, _, st = trk.trajectory()
+    sha = hashlib.sha1(np.ascontiguousarray(poses).tobytes()).hexdigest()
+    walls = []
+    trk.profile(True)
+    for _ in range(reps):
+        t1 = time.time()
+        step()
+        walls.append((time.time() - t1) * 1e3)
+    ms, n = trk.profile_read()
+    trk.profile(False)
+    names = {0: "k_ingest", 1: "k_normals", 2: "k_icp_L0", 3: "k_icp_L1", 4: "k_icp_L2", 7: "k_compose"}
+    per = {names[k]: round(float(ms[k]) / reps, 4) for k in names if n[k]}
+    print(json.dumps({"lib": name, "frames": frames_n, "trajectory_sha1": sha, "lost": int((st & 2 != 0).sum()),
+                      "ms_per_step_by_kernel": per, "sum_ms": round(sum(per.values()), 4),
+                      "wall_ms_per_profiled_step_from_host_frames": round(min(walls), 3), "init_s": round(t_init, 2)}), flush=True)
+    lib.youth_cuda_host_free(pinned)
+    trk.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=300)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--child", default=None)
+    ap.add_argument("names", nargs="*", default=["default", "xy3", "xy1", "xy2", "fastdiv"])
+    args = ap.parse_args()
+    if args.child:
+        return child(args.child, args.frames, args.reps)
+    import youth_pkg
+
+    pkg = youth_pkg.load()
+    np.save(SHM, pkg.synth_sequence(args.frames))
+    vdir = os.path.join(ROOT, "slam-rgbd_b200", "lib", "variants")
+    for name in args.names:
+        env = dict(os.environ)
+        env.pop("YOUTH_CUDA_LIB", None)
+        if name != "default":
+            so = os.path.join(vdir, f"libyouth_cuda_{name}.so")
+            if not os.path.exists(so):
+                print(json.dumps({"lib": name, "error": "not built"}), flush=True)
+                continue
+            env["YOUTH_CUDA_LIB"] = so
+        res = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", name, "--frames", str(args.frames),
+                              "--reps", str(args.reps)], env=env, capture_output=True, text=True)
+        sys.stdout.write(res.stdout)
+        if res.returncode != 0:
+            print(json.dumps({"lib": name, "error": res.stderr[-600:]}), flush=True)
+        sys.stdout.flush()
+    try:
+        os.remove(SHM)
+    except OSError:
+        pass
+
+
+if __name__ == "__main__":
+    main()
