@@ -112,6 +112,15 @@ int main() {
   CK(cudaMalloc(&base, (size_t)FRAMES * NPIX * 32));
   CK(cudaMemset(base, 0, (size_t)FRAMES * NPIX * 32));
   CK(cudaMalloc(&out, 1 << 22));
+  /* the depth x occupancy points of the k_icp variants (make next-variants): 20 warps x 2 (today), 16 x 3, 12 x 4,
+   * 12 x 5, 12 x 6 pixels in flight per lane, three-plane and two-plane records, ppr 128 as bench.py runs */
+  run<2, 2, 2>(base, out, 128, 5);
+  run<2, 3, 3>(base, out, 128, 4);
+  run<2, 4, 4>(base, out, 128, 3);
+  run<3, 2, 2>(base, out, 128, 5);
+  run<3, 3, 3>(base, out, 128, 4);
+  run<3, 5, 5>(base, out, 128, 3);
+  run<3, 6, 6>(base, out, 128, 3);
   for (int ppr : {32, 64}) {
     for (int bps : {5, 6, 8, 12}) {
       run<0, 1, 1>(base, out, ppr, bps);
