@@ -689,7 +689,8 @@ def run_ours(args):
                      "note": "algorithmic 48 B/px/iter = the bytes k_icp requests (three float2 planes per frame, "
                              "24 B/px); each frame's second use in a launch hits L2, so DRAM traffic is about half "
                              "(traffic = ncu dram bytes per launch, profiles/traffic.json); a fraction above 1 is L2 reuse, "
-                             "see DESIGN.md section 5"},
+                             "see DESIGN.md section 5; the kernel is latency-bound, not bandwidth-bound: its rate is resident "
+                             "lanes x 2 pixels in flight / loaded memory latency (DESIGN.md section 12, item 0a)"},
         "roofline_k_ingest": ingest_roof,
         "per_kernel_ms_per_step": step_prof,
         "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": threads, "kind": "port",
