@@ -11,7 +11,7 @@ V=slam-rgbd_b200/lib/variants
 # the opt-in GPU leg of the mq: mode (first run)
 YOUTH_TEST_MQ_MODE=1 timeout 300 python -m pytest tests/test_live_pipeline.py -x -q -m gpu > gpurun_out/mq_mode_test.log 2>&1; echo "mq mode test rc=$?"
 python tools/variant_probe.py > gpurun_out/variant_probe.jsonl 2> gpurun_out/variant_probe.err; cat gpurun_out/variant_probe.jsonl | cut -c1-330
-for name in default d3mb4 d4mb3 d4mb4xy3slim d5mb3xy3 d6mb3xy3; do
+for name in default s8d2mb5 s8d3mb4 s8d4mb4 d3mb4 d4mb3 d4mb4xy3slim d5mb3xy3 d6mb3xy3; do
   if [ "$name" = default ]; then unset YOUTH_CUDA_LIB; else
     [ -f "$V/libyouth_cuda_$name.so" ] || { echo "$name: not built"; continue; }
     export YOUTH_CUDA_LIB="$PWD/$V/libyouth_cuda_$name.so"
