@@ -221,6 +221,48 @@ def track_sequence(cfg, frames, fast=False):
     return poses, status, secs
 
 
+def track_sequence_parallel(cfg, frames, threads=None, fast=False):
+    """yo_track_sequence with the independent frame pairs spread over host threads: every frame is preprocessed
+    once (yo_preprocess), every pair tracked from the identity (yo_track_pair), and the pose chain composed in
+    frame order (yo_compose) -- the same calls in the same per-pair order as yo_tracker_track, so the result is
+    bit-identical to track_sequence (tests/test_oracle.py checks it).  Returns (poses f32 [n][12], status u32 [n],
+    inliers i32 [n], seconds)."""
+    import concurrent.futures
+    import time
+
+    assert frames.dtype == np.uint16 and frames.flags.c_contiguous
+    n = frames.shape[0]
+    L = lib(fast)
+    threads = max(1, min(threads or (os.cpu_count() or 1), n))
+    t0 = time.perf_counter()
+    ofr = [None] * n
+
+    def prep(i):
+        ofr[i] = OFrame(cfg, frames[i], fast=fast)
+
+    rel = np.zeros((n, 12), dtype=np.float64)
+    st = np.zeros(n, dtype=np.uint32)
+    inl = np.zeros(n, dtype=np.int32)
+
+    def pair(i):
+        v = C.c_int32()
+        st[i] = L.yo_track_pair(C.byref(cfg), ofr[i].ptr, ofr[i - 1].ptr, rel[i].ctypes.data, C.byref(v))
+        inl[i] = v.value
+
+    with concurrent.futures.ThreadPoolExecutor(threads) as ex:
+        list(ex.map(prep, range(n)))
+        list(ex.map(pair, range(1, n)))
+    world = np.zeros(12, dtype=np.float64)
+    world[[0, 5, 10]] = 1.0
+    poses = np.empty((n, 12), dtype=np.float32)
+    st[0] = 1  # YO_STATUS_FIRST
+    for i in range(n):
+        if i:
+            L.yo_compose(world.ctypes.data, rel[i].ctypes.data, world.ctypes.data)
+        poses[i] = world.astype(np.float32)
+    return poses, st, inl, time.perf_counter() - t0
+
+
 def codec_encode(frame):
     """uint16 [H][W] -> packed bytes (numpy uint8) with the CPU statement of the YD16 codec."""
     assert frame.dtype == np.uint16 and frame.flags.c_contiguous

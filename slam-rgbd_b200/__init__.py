@@ -16,6 +16,7 @@ from .binding import (  # noqa: F401
     cuda_lib,
     lib_paths,
     synth_gt,
+    synth_lib,
     synth_sequence,
     tsdf_config,
 )

@@ -69,12 +69,37 @@ def lib_paths():
         # YOUTH_CUDA_LIB: A/B builds of the same source (tools/ only); never a non-CUDA substitute
         "cuda": os.environ.get("YOUTH_CUDA_LIB") or os.path.join(PKG_DIR, "lib", "libyouth_cuda.so"),
         "host": os.path.join(PKG_DIR, "lib", "libAlgorithmModule.so"),
+        "synth": os.path.join(PKG_DIR, "lib", "libyouth_synth.so"),
         "harness": os.path.join(PKG_DIR, "bin", "youth_harness"),
     }
 
 
 _cuda = None
 _host = None
+_synth = None
+
+
+def synth_lib():
+    """The synthetic sequence generator (host/youth_synth.c) as a library of its own: plain C, links no CUDA, so
+    callers that must not map the GPU code (bench.py --impl reference) can still generate the workload."""
+    global _synth
+    if _synth is not None:
+        return _synth
+    path = lib_paths()["synth"]
+    if not os.path.exists(path):
+        raise CudaLibraryMissing(f"{path} is missing: build the package first")
+    L = C.CDLL(path)
+    SC = C.POINTER(SynthConfig)
+    for name, (res, args) in {
+        "youth_synth_default": (None, [SC, C.c_int, C.c_int, C.c_int]),
+        "youth_synth_gt": (None, [SC, C.c_int, C.c_void_p]),
+        "youth_synth_sequence": (None, [SC, C.c_int, C.c_int, C.c_void_p]),
+    }.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _synth = L
+    return L
 
 
 def cuda_lib():
@@ -192,6 +217,8 @@ def host_lib():
         "youthSlamDrain": (None, []),
         "youthSlamGetTrajectory": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
         "youthSlamStats": (None, [C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_long)]),
+        "youthSlamAcquireSlot": (C.c_void_p, [C.c_int, C.c_int]),
+        "youthSlamCommitSlot": (C.c_int, [C.c_uint32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -229,7 +256,7 @@ def tsdf_config(**overrides) -> TsdfConfig:
 
 def synth_config(width=640, height=480, sequence=0, noise=0) -> SynthConfig:
     sc = SynthConfig()
-    host_lib().youth_synth_default(C.byref(sc), width, height, sequence)
+    synth_lib().youth_synth_default(C.byref(sc), width, height, sequence)
     sc.noise = noise
     return sc
 
@@ -238,7 +265,7 @@ def synth_sequence(n, width=640, height=480, sequence=0, noise=0, first=0) -> np
     """uint16 [n][height][width] synthetic depth (mm) from the C generator."""
     sc = synth_config(width, height, sequence, noise)
     out = np.empty((n, height, width), dtype=np.uint16)
-    host_lib().youth_synth_sequence(C.byref(sc), first, n, out.ctypes.data)
+    synth_lib().youth_synth_sequence(C.byref(sc), first, n, out.ctypes.data)
     return out
 
 
@@ -247,7 +274,7 @@ def synth_gt(n, width=640, height=480, sequence=0) -> np.ndarray:
     sc = synth_config(width, height, sequence)
     out = np.empty((n, 12), dtype=np.float64)
     for i in range(n):
-        host_lib().youth_synth_gt(C.byref(sc), i, out[i].ctypes.data)
+        synth_lib().youth_synth_gt(C.byref(sc), i, out[i].ctypes.data)
     return out
 
 

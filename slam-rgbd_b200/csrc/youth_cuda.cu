@@ -29,7 +29,7 @@
 #define YK_GRAPH_MAX_N 8   /* groups of at most this many frames per stream run as one captured CUDA graph */
 #define YK_GRAPH_SLOTS (2 * YK_GRAPH_MAX_N)
 #define YK_ICP_QUEUES 8
-#define YK_TICKETS 16
+#define YK_TICKETS (4 * YK_MAX_STREAMS) /* two steps in flight with one read per stream each, twice over */
 #define YK_ICP_LAST_CTA_MAX_CTAS 444 /* one wave of the 152-register variant: 3 CTAs on each of 148 SMs */
 
 /* ------------------------------------------------------------------ errors */
@@ -1431,7 +1431,9 @@ extern "C" int youth_cuda_read_last_inliers_async(youth_cuda_handle* h, int stre
 extern "C" int youth_cuda_wait_ticket(youth_cuda_handle* h, uint64_t ticket) {
   if (!h) return fail("null handle");
   if (ticket >= h->ticket_next) return fail("unknown ticket");
-  if (ticket + YK_TICKETS < h->ticket_next) return 1; /* its event was re-used by a later read on the same stream: long done or covered */
+  /* When more than YK_TICKETS reads were issued since, the slot holds the event of a LATER read.  Every read is
+   * recorded on the same stream, so that event completes after this ticket's copies: waiting for it covers the
+   * ticket (never return without a wait -- the caller is about to read the destination buffers). */
   CU(cudaSetDevice(h->cfg.device));
   CU(cudaEventSynchronize(h->ticket_ev[ticket % YK_TICKETS]));
   return 1;

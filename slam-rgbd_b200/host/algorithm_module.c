@@ -19,11 +19,7 @@
 
 #include "algorithmModule.h"
 #include "youth_host.h"
-
-void youthSlamSetOptions(int lossless, int batch);
-void youthSlamDrain(void);
-int youthSlamProcessPackedFrames(const uint8_t* streams, const uint64_t* offsets, int n, int width, int height,
-                                 const uint32_t* timestamps);
+#include "youth_slam_ext.h"
 
 #define PACKED_RUN 64 /* packed records are gathered into runs of this many frames */
 

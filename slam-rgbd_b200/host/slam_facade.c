@@ -26,22 +26,36 @@
 #include <time.h>
 
 #include "SLAM.h"
+#include "youth_slam_ext.h"
 #include "youth_host.h"
 #include "youth_model.h"
 
 #define QUEUE_HIGH_WATER 10 /* SLAM.cpp:163 */
 #define QUEUE_LOW_WATER 5   /* SLAM.cpp:165 */
+#define MAX_GROUP 512       /* frames per launch group (youthSlamSetOptions / YOUTH_SLAM_BATCH) */
 
+/* The host frame ring.  Positions are absolute frame counters (slot = position % qcap):
+ *     done <= head <= tail,   tail - done < qcap
+ *   [done, head)  handed to the tracker and not collected yet (or dropped while such a run was in flight)
+ *   [head, tail)  published, waiting for the worker
+ *   tail          the slot a producer is filling right now (`filling`), published by the commit
+ * A producer reserves the slot under the mutex, fills it WITHOUT the mutex (614 KB per VGA frame: the worker
+ * claims and collects runs meanwhile) and publishes it under the mutex.  Space is accounted from `done`, so the
+ * write position cannot run round into frames the tracker still reads. */
 static struct {
   pthread_mutex_t mu;
-  pthread_cond_t nonempty, nonfull, idle;
+  pthread_cond_t nonempty, nonfull, idle, prod;
   atomic_int running;
   atomic_int stop_req;
+  atomic_int failed; /* sticky: the tracker refused a run (e.g. trajectory capacity exhausted); cleared by resetSlam */
   youth_cuda_handle* h;
   youth_cuda_config cfg;
   uint16_t* ring; /* pinned, qcap frames */
   uint32_t* ts;
-  int qcap, head, count, busy; /* count = frames waiting; busy = claimed by the worker, slots still in use */
+  int qcap;
+  uint64_t done, head, tail;
+  int inflight; /* frames in runs handed to the tracker and not collected */
+  int filling;  /* a producer holds the slot at `tail` */
   int lossless, batch;
   pthread_t worker;
   long accepted, dropped, tracked, poses_sent;
@@ -52,11 +66,13 @@ static struct {
        .nonempty = PTHREAD_COND_INITIALIZER,
        .nonfull = PTHREAD_COND_INITIALIZER,
        .idle = PTHREAD_COND_INITIALIZER,
+       .prod = PTHREAD_COND_INITIALIZER,
        .lossless = -1,
        .batch = -1,
        .pose_mq = (mqd_t)-1};
 
 static size_t frame_px(void) { return (size_t)G.cfg.width * (size_t)G.cfg.height; }
+static int waiting(void) { return (int)(G.tail - G.head); }
 
 /* The synchronous copy-in of processSlamFrame (SLAM.cpp:133-134) is what bounds the facade's frame rate: one
  * caller thread moving 614 KB per VGA frame into a ring far larger than the caches.  The ring is read next by
@@ -92,44 +108,59 @@ static void copy_in(void* dst, const void* src, size_t bytes) { memcpy(dst, src,
  * With an empty queue it collects at once, so a lone live frame is not delayed. */
 typedef struct {
   int valid, ok, n, first, base, buf;
+  uint64_t pos; /* ring position of the run's first frame */
   uint64_t ticket;
 } PendingRun;
 
-static void collect_run(const PendingRun* r, float* const poses[2], int* const inl[2]) {
+/* next: the run submitted after r (still in flight), or NULL */
+static void collect_run(const PendingRun* r, const PendingRun* next, float* const poses[2], uint32_t* const status[2],
+                        int* const inl[2]) {
   long sent = 0;
   int ok = r->ok;
   if (ok && !youth_cuda_wait_ticket(G.h, r->ticket)) {
     fprintf(stderr, "AlgorithmModule: tracking failed: %s\n", youth_cuda_last_error());
     ok = 0;
   }
+  if (!ok) {
+    /* work of this run may have been enqueued before the failure (H2D copies out of the ring slots): nothing
+     * is released before the device is idle */
+    youth_cuda_sync(G.h);
+    atomic_store(&G.failed, 1);
+  }
   if (ok) {
     atomic_store(&G.last_inliers, *inl[r->buf]);
     if (G.pose_mq != (mqd_t)-1) {
       /* pose egress: one MSG_TYPE_POSE message per tracked frame on the
-       * logger->viewer queue; non-blocking, a full queue drops the pose rather than stalling tracking */
+       * logger->viewer queue; non-blocking, a full queue drops the pose rather than stalling tracking.
+       * status = the frame's own YOUTH_STATUS_* bits; inliers = the inlier count of the run's LAST frame (the
+       * tracker keeps one count per sequence, not per frame) */
       const uint32_t in = (uint32_t)*inl[r->buf];
       char msg[sizeof(MessageHeader) + sizeof(YouthPoseMsg)];
       for (int i = 0; i < r->n; ++i) {
-        const size_t len = youth_pose_msg_build(msg, r->base + i, G.ts[r->first + i], poses[r->buf] + 12 * (size_t)i, 0u, in);
+        const size_t len = youth_pose_msg_build(msg, r->base + i, G.ts[r->first + i], poses[r->buf] + 12 * (size_t)i,
+                                                status[r->buf][i], in);
         if (mq_send(G.pose_mq, msg, len, 0) == 0) ++sent;
       }
     }
   }
   pthread_mutex_lock(&G.mu);
-  G.busy -= r->n;
+  G.inflight -= r->n;
+  G.done = (next && next->valid) ? next->pos : G.head; /* runs complete in order */
   G.poses_sent += sent;
   G.tracked += ok ? r->n : 0;
   pthread_cond_broadcast(&G.nonfull);
-  if (G.count == 0 && G.busy == 0) pthread_cond_broadcast(&G.idle);
+  if (waiting() == 0 && G.inflight == 0) pthread_cond_broadcast(&G.idle);
   pthread_mutex_unlock(&G.mu);
 }
 
 static void* worker_main(void* arg) {
   (void)arg;
   float* poses[2];
+  uint32_t* status[2];
   int* inl[2];
   for (int k = 0; k < 2; ++k) {
     poses[k] = (float*)youth_cuda_host_alloc(sizeof(float) * 12 * (size_t)G.batch);
+    status[k] = (uint32_t*)youth_cuda_host_alloc(sizeof(uint32_t) * (size_t)G.batch);
     inl[k] = (int*)youth_cuda_host_alloc(sizeof(int));
   }
   PendingRun pend;
@@ -137,20 +168,20 @@ static void* worker_main(void* arg) {
   int turn = 0;
   for (;;) {
     pthread_mutex_lock(&G.mu);
-    while (G.count == 0 && !pend.valid && !atomic_load(&G.stop_req)) pthread_cond_wait(&G.nonempty, &G.mu);
-    if (G.count == 0 && !pend.valid) { /* stop requested and everything collected */
+    while (waiting() == 0 && !pend.valid && !atomic_load(&G.stop_req)) pthread_cond_wait(&G.nonempty, &G.mu);
+    if (waiting() == 0 && !pend.valid) { /* stop requested and everything collected */
       pthread_mutex_unlock(&G.mu);
       break;
     }
     /* claim the longest run of consecutive slots: contiguous in the pinned ring, at most
-     * one batch.  Claimed frames leave the queue at once; `busy` fences their slots. */
-    int n = G.count;
+     * one batch.  Claimed frames leave the queue at once; [done, head) fences their slots. */
+    int n = waiting();
     if (n > G.batch) n = G.batch;
-    if (n > G.qcap - G.head) n = G.qcap - G.head;
-    const int first = G.head;
-    G.head = (G.head + n) % G.qcap;
-    G.count -= n;
-    G.busy += n;
+    const int first = (int)(G.head % (uint64_t)G.qcap);
+    if (n > G.qcap - first) n = G.qcap - first;
+    const uint64_t pos = G.head;
+    G.head += (uint64_t)n;
+    G.inflight += n;
     pthread_mutex_unlock(&G.mu);
 
     PendingRun cur;
@@ -160,21 +191,23 @@ static void* worker_main(void* arg) {
       cur.valid = 1;
       cur.n = n;
       cur.first = first;
+      cur.pos = pos;
       cur.buf = turn;
       turn ^= 1;
       cur.ok = youth_cuda_track_batch(G.h, src, n, YOUTH_MEM_HOST_PINNED, G.ts + first, NULL);
       cur.base = youth_cuda_frame_count(G.h, 0) - n;
       if (cur.ok) {
         cur.ok = youth_cuda_read_last_inliers_async(G.h, 0, inl[cur.buf]) &&
-                 youth_cuda_read_trajectory_async(G.h, 0, cur.base, n, poses[cur.buf], NULL, &cur.ticket) == n;
+                 youth_cuda_read_trajectory_async(G.h, 0, cur.base, n, poses[cur.buf], status[cur.buf], &cur.ticket) == n;
       }
       if (!cur.ok) fprintf(stderr, "AlgorithmModule: tracking failed: %s\n", youth_cuda_last_error());
     }
-    if (pend.valid) collect_run(&pend, poses, inl);
+    if (pend.valid) collect_run(&pend, &cur, poses, status, inl);
     pend = cur;
   }
   for (int k = 0; k < 2; ++k) {
     youth_cuda_host_free(poses[k]);
+    youth_cuda_host_free(status[k]);
     youth_cuda_host_free(inl[k]);
   }
   return NULL;
@@ -198,7 +231,7 @@ void initSlamModule(const char* config_file, const char* vocabulary_file) {
     const char* e = getenv("YOUTH_SLAM_BATCH");
     G.batch = e ? atoi(e) : 8;
     if (G.batch < 1) G.batch = 1;
-    if (G.batch > 64) G.batch = 64;
+    if (G.batch > MAX_GROUP) G.batch = MAX_GROUP;
   }
   const char* dev = getenv("YOUTH_SLAM_DEVICE");
   G.cfg.device = dev ? atoi(dev) : 0;
@@ -230,7 +263,8 @@ void initSlamModule(const char* config_file, const char* vocabulary_file) {
       atomic_store(&G.model_on, 1);
     }
   }
-  G.qcap = QUEUE_HIGH_WATER + 2 + 3 * G.batch; /* queue + the two runs in flight always fit */
+  /* the waiting frames, the slot being filled, two runs in flight and one more being assembled always fit */
+  G.qcap = QUEUE_HIGH_WATER + 4 + 3 * G.batch;
   G.ring = (uint16_t*)youth_cuda_host_alloc(frame_px() * sizeof(uint16_t) * (size_t)G.qcap);
   G.ts = (uint32_t*)calloc((size_t)G.qcap, sizeof(uint32_t));
   if (!G.ring || !G.ts) {
@@ -243,7 +277,8 @@ void initSlamModule(const char* config_file, const char* vocabulary_file) {
     G.ts = NULL;
     return;
   }
-  G.head = G.count = G.busy = 0;
+  G.done = G.head = G.tail = 0;
+  G.inflight = G.filling = 0;
   G.accepted = G.dropped = G.tracked = G.poses_sent = 0;
   G.pose_mq = (mqd_t)-1;
   {
@@ -260,6 +295,7 @@ void initSlamModule(const char* config_file, const char* vocabulary_file) {
   }
   atomic_store(&G.last_inliers, 0);
   atomic_store(&G.stop_req, 0);
+  atomic_store(&G.failed, 0);
   if (pthread_create(&G.worker, NULL, worker_main, NULL) != 0) {
     fprintf(stderr, "AlgorithmModule: cannot start the worker thread\n");
     youth_cuda_host_free(G.ring);
@@ -283,10 +319,13 @@ void stopSlamModule(void) {
   atomic_store(&G.stop_req, 1);
   pthread_cond_broadcast(&G.nonempty);
   pthread_cond_broadcast(&G.nonfull);
+  pthread_cond_broadcast(&G.prod);
+  /* a producer that holds a ring slot finishes (its commit sees stop_req and discards the frame) */
+  while (G.filling) pthread_cond_wait(&G.prod, &G.mu);
   pthread_mutex_unlock(&G.mu);
   pthread_join(G.worker, NULL); /* the worker drains what is queued before leaving */
   /* a producer that passed the `running` test before stop_req was set either holds the mutex now (wait for it
-   * to leave the ring) or will see stop_req once it has it */
+   * to leave) or will see stop_req once it has it */
   pthread_mutex_lock(&G.mu);
   atomic_store(&G.running, 0);
   youth_cuda_handle* h = G.h; /* threads that waited for the idle worker under the mutex find no handle from here on */
@@ -305,43 +344,102 @@ void stopSlamModule(void) {
   }
 }
 
-int processSlamFrame(const int16_t* depth_data, const uint8_t* color_data, int width, int height, uint32_t timestamp) {
-  (void)color_data; /* depth-only tracker; colour passes through the pipeline untouched */
-  if (!atomic_load(&G.running) || !depth_data) return 0;
-  if (width != G.cfg.width || height != G.cfg.height) return 0;
+/* ---- producer side: reserve a ring slot, fill it, publish it ---- */
+
+/* Reserve the next ring slot for a frame of the configured size and return its address in page-locked host
+ * memory, NULL when no frame can be taken (module not running / stopping / failed, wrong size; lossy mode with
+ * the ring physically full: the frame counts as accepted-and-dropped).  The caller fills width*height uint16
+ * depth values (mm) and calls youthSlamCommitSlot(); one slot is outstanding at a time -- a second producer
+ * waits here until the first has committed.  This is the zero-copy form of processSlamFrame(): a producer that
+ * assembles frames anyway (the logger's chunk reassembly, loggingModule.c:303-327; a file reader) writes them
+ * where the copy engine reads them, instead of into a buffer of its own that processSlamFrame() then copies. */
+uint16_t* youthSlamAcquireSlot(int width, int height) {
+  if (!atomic_load(&G.running) || atomic_load(&G.failed)) return NULL;
+  if (width != G.cfg.width || height != G.cfg.height) return NULL;
   pthread_mutex_lock(&G.mu);
+  while (G.filling && !atomic_load(&G.stop_req)) pthread_cond_wait(&G.prod, &G.mu);
   if (G.lossless)
-    while (G.count + G.busy >= G.qcap && !atomic_load(&G.stop_req)) pthread_cond_wait(&G.nonfull, &G.mu);
-  if (atomic_load(&G.stop_req) || !G.ring) { /* stopSlamModule() is under way or done: the ring is (about to be) released */
+    while (G.tail - G.done >= (uint64_t)G.qcap - 1 && !atomic_load(&G.stop_req) && !atomic_load(&G.failed))
+      pthread_cond_wait(&G.nonfull, &G.mu);
+  if (atomic_load(&G.stop_req) || atomic_load(&G.failed) || !G.ring) { /* stopSlamModule() is under way or done */
+    pthread_mutex_unlock(&G.mu);
+    return NULL;
+  }
+  if (!G.lossless && waiting() > QUEUE_HIGH_WATER) {
+    /* SLAM.cpp:163-167: more than 10 waiting -> drop the oldest down to 5.  The survivors (the newest 5, six or
+     * more slots further on, so source and destination never overlap) move down to the head of the queue: the
+     * ring keeps the shape [in flight][waiting][free], runs stay contiguous, and the write position can never
+     * run round into frames the tracker still reads however much faster than the tracker the producer is.
+     * (3 MB of copies under the mutex, only on the overloaded lossy path; no producer is filling a slot now.) */
+    const int drop = waiting() - QUEUE_LOW_WATER;
+    for (int k = 0; k < QUEUE_LOW_WATER; ++k) {
+      const size_t from = (size_t)((G.head + (uint64_t)(drop + k)) % (uint64_t)G.qcap), to = (size_t)((G.head + (uint64_t)k) % (uint64_t)G.qcap);
+      memcpy(G.ring + frame_px() * to, G.ring + frame_px() * from, frame_px() * sizeof(uint16_t));
+      G.ts[to] = G.ts[from];
+    }
+    G.tail = G.head + QUEUE_LOW_WATER;
+    G.dropped += drop;
+  }
+  if (G.tail - G.done >= (uint64_t)G.qcap - 1) { /* cannot happen in the lossy mode (at most 11 waiting + two runs in flight) */
+    G.accepted++;
+    G.dropped++;
+    pthread_mutex_unlock(&G.mu);
+    return NULL;
+  }
+  G.filling = 1;
+  uint16_t* slot = G.ring + frame_px() * (size_t)(G.tail % (uint64_t)G.qcap);
+  pthread_mutex_unlock(&G.mu);
+  return slot;
+}
+
+/* Publish the slot returned by the last youthSlamAcquireSlot().  1 = queued for tracking, 0 = discarded (no slot
+ * outstanding, or the module is stopping). */
+int youthSlamCommitSlot(uint32_t timestamp) {
+  pthread_mutex_lock(&G.mu);
+  if (!G.filling) {
     pthread_mutex_unlock(&G.mu);
     return 0;
   }
-  if (!G.lossless && G.count > QUEUE_HIGH_WATER) {
-    /* SLAM.cpp:163-167: more than 10 waiting -> drop the oldest down to 5.  The survivors move down to the
-     * head of the queue (they are the newest 5, six or more slots further on, so source and destination never
-     * overlap): the ring keeps the shape [in flight][waiting][free] and the slot written below can never be one
-     * the tracker is still reading -- skipping over the dropped slots instead would let the write position
-     * run round into them when the tracker is slower than the producer. */
-    const int drop = G.count - QUEUE_LOW_WATER;
-    for (int k = 0; k < QUEUE_LOW_WATER; ++k) {
-      const int from = (G.head + drop + k) % G.qcap, to = (G.head + k) % G.qcap;
-      memcpy(G.ring + frame_px() * (size_t)to, G.ring + frame_px() * (size_t)from, frame_px() * sizeof(uint16_t));
-      G.ts[to] = G.ts[from];
-    }
-    G.count = QUEUE_LOW_WATER;
-    G.dropped += drop;
+  int ok = 0;
+  if (!atomic_load(&G.stop_req) && G.ring) {
+    G.ts[G.tail % (uint64_t)G.qcap] = timestamp;
+    G.tail++;
+    G.accepted++;
+    if (waiting() == 1) pthread_cond_signal(&G.nonempty); /* the worker only sleeps on an empty queue */
+    ok = 1;
   }
-  /* count <= 11 and at most two runs of `batch` frames in flight: count + busy < qcap, the slot is free */
-  const int slot = (G.head + G.count) % G.qcap;
-  /* reference depth is int16_t; values >= 32768 are reinterpreted as uint16 like the
-   * CV_16UC1 view at SLAM.cpp:133 and then rejected by the depth_max gate */
-  copy_in(G.ring + frame_px() * (size_t)slot, depth_data, frame_px() * sizeof(uint16_t));
-  G.ts[slot] = timestamp;
-  G.count++;
-  G.accepted++;
-  if (G.count == 1) pthread_cond_signal(&G.nonempty); /* the worker only sleeps on an empty queue */
+  G.filling = 0;
+  pthread_cond_broadcast(&G.prod);
   pthread_mutex_unlock(&G.mu);
-  return 1;
+  return ok;
+}
+
+int processSlamFrame(const int16_t* depth_data, const uint8_t* color_data, int width, int height, uint32_t timestamp) {
+  (void)color_data; /* depth-only tracker; colour passes through the pipeline untouched */
+  if (!depth_data) return 0;
+  if (!atomic_load(&G.running) || width != G.cfg.width || height != G.cfg.height) return 0;
+  long dropped_before = 0;
+  if (!G.lossless) {
+    pthread_mutex_lock(&G.mu);
+    dropped_before = G.dropped;
+    pthread_mutex_unlock(&G.mu);
+  }
+  uint16_t* slot = youthSlamAcquireSlot(width, height);
+  if (!slot) {
+    /* lossy mode with a full ring: the frame was accepted and dropped, like any other dropped frame */
+    int was_dropped = 0;
+    if (!G.lossless && atomic_load(&G.running) && !atomic_load(&G.stop_req) && !atomic_load(&G.failed)) {
+      pthread_mutex_lock(&G.mu);
+      was_dropped = G.dropped > dropped_before;
+      pthread_mutex_unlock(&G.mu);
+    }
+    return was_dropped;
+  }
+  /* the synchronous copy of SLAM.cpp:133-134, outside the mutex: the caller may reuse its buffer on return.
+   * reference depth is int16_t; values >= 32768 are reinterpreted as uint16 like the CV_16UC1 view at
+   * SLAM.cpp:133 and then rejected by the depth_max gate */
+  copy_in(slot, depth_data, frame_px() * sizeof(uint16_t));
+  return youthSlamCommitSlot(timestamp);
 }
 
 /* ---- additions for headless drivers (not in the reference facade) ---- */
@@ -350,7 +448,7 @@ int processSlamFrame(const int16_t* depth_data, const uint8_t* color_data, int w
  * Call before initSlamModule; -1 keeps the environment/default choice. */
 void youthSlamSetOptions(int lossless, int batch) {
   if (lossless >= 0) G.lossless = lossless ? 1 : 0;
-  if (batch >= 1) G.batch = batch > 64 ? 64 : batch;
+  if (batch >= 1) G.batch = batch > MAX_GROUP ? MAX_GROUP : batch;
 }
 
 /* The tracker handle is used by the worker thread; other threads touch it only while the worker has nothing
@@ -358,14 +456,14 @@ void youthSlamSetOptions(int lossless, int batch) {
  * processSlamFrame for that long). */
 static void lock_idle(void) {
   pthread_mutex_lock(&G.mu);
-  while (G.count > 0 || G.busy > 0) pthread_cond_wait(&G.idle, &G.mu);
+  while (waiting() > 0 || G.inflight > 0) pthread_cond_wait(&G.idle, &G.mu);
 }
 
 /* wait until every accepted frame has been tracked */
 void youthSlamDrain(void) {
   if (!atomic_load(&G.running)) return;
   pthread_mutex_lock(&G.mu);
-  while (G.count > 0 || G.busy > 0) pthread_cond_wait(&G.idle, &G.mu);
+  while (waiting() > 0 || G.inflight > 0) pthread_cond_wait(&G.idle, &G.mu);
   pthread_mutex_unlock(&G.mu);
 }
 
@@ -377,7 +475,12 @@ int youthSlamProcessPackedFrames(const uint8_t* streams, const uint64_t* offsets
   if (!atomic_load(&G.running) || !streams || !offsets || n < 1) return 0;
   if (width != G.cfg.width || height != G.cfg.height) return 0;
   float* poses = (float*)malloc(sizeof(float) * 12 * (size_t)G.batch);
-  if (!poses) return 0;
+  uint32_t* status = (uint32_t*)calloc((size_t)G.batch, sizeof(uint32_t));
+  if (!poses || !status) {
+    free(poses);
+    free(status);
+    return 0;
+  }
   lock_idle(); /* the worker is idle: the handle is ours */
   int ok = G.h != NULL;
   for (int f0 = 0; f0 < n && ok; f0 += G.batch) {
@@ -395,16 +498,18 @@ int youthSlamProcessPackedFrames(const uint8_t* streams, const uint64_t* offsets
     if (G.pose_mq != (mqd_t)-1) {
       const int base = youth_cuda_frame_count(G.h, 0) - cn;
       const uint32_t inl = (uint32_t)atomic_load(&G.last_inliers);
+      if (youth_cuda_get_trajectory(G.h, 0, base, cn, NULL, NULL, status) != cn) memset(status, 0, sizeof(uint32_t) * (size_t)cn);
       char msg[sizeof(MessageHeader) + sizeof(YouthPoseMsg)];
       for (int i = 0; i < cn; ++i) {
         const size_t len = youth_pose_msg_build(msg, base + i, timestamps ? timestamps[f0 + i] : 0u,
-                                                poses + 12 * (size_t)i, 0u, inl);
+                                                poses + 12 * (size_t)i, status[i], inl);
         if (mq_send(G.pose_mq, msg, len, 0) == 0) G.poses_sent++;
       }
     }
   }
   pthread_mutex_unlock(&G.mu);
   free(poses);
+  free(status);
   return ok;
 }
 
@@ -491,5 +596,6 @@ void resetSlam(void) {
   lock_idle();
   if (G.h) youth_cuda_reset(G.h, -1);
   atomic_store(&G.last_inliers, 0);
+  atomic_store(&G.failed, 0); /* the trajectory is empty again: the tracker can take frames */
   pthread_mutex_unlock(&G.mu);
 }

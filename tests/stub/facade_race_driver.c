@@ -4,7 +4,9 @@
  * tracker behind the facade is the test double (youth_cuda_stub.c).  Scenarios, each in both queue modes:
  *   a producer pushing frames while the main thread stops the module;
  *   a producer + a status reader (isSlamModuleRunning / getSlamMapPoints / youthSlamStats) + drain, reset,
- *   saveSlamMap from the main thread, then stop.
+ *   saveSlamMap from the main thread, then stop;
+ *   the same with a SECOND producer that uses the zero-copy calls (youthSlamAcquireSlot / youthSlamCommitSlot)
+ *   at the same time as the first one calls processSlamFrame.
  * usage: facade_race_driver <config.yaml> <out_prefix>
  */
 #define _GNU_SOURCE
@@ -16,10 +18,8 @@
 #include <unistd.h>
 
 #include "SLAM.h"
+#include "youth_slam_ext.h"
 
-void youthSlamSetOptions(int lossless, int batch);
-void youthSlamDrain(void);
-void youthSlamStats(long* accepted, long* dropped, long* tracked);
 long stub_torn_frames(void);
 
 enum { W = 64, H = 48 };
@@ -39,6 +39,23 @@ static void* producer(void* arg) {
   return NULL;
 }
 
+/* fills the ring slot in place: the frame is born in the page-locked ring */
+static void* producer_zero_copy(void* arg) {
+  long* pushed = (long*)arg;
+  for (uint32_t i = 0; !atomic_load(&g_quit); ++i) {
+    uint16_t* slot = youthSlamAcquireSlot(W, H);
+    if (slot) {
+      memset(slot, 0, (size_t)W * H * sizeof(uint16_t));
+      slot[0] = slot[W * H - 1] = (uint16_t)(i & 0x7fff);
+      if (youthSlamCommitSlot(i)) ++*pushed;
+    } else if (!isSlamModuleRunning()) {
+      break;
+    }
+    if (g_pace_us) usleep((useconds_t)g_pace_us);
+  }
+  return NULL;
+}
+
 static void* reader(void* arg) {
   (void)arg;
   long a, d, t, sink = 0;
@@ -54,7 +71,7 @@ static void* reader(void* arg) {
 int main(int argc, char** argv) {
   if (argc < 3) return 2;
   setenv("YOUTH_STUB_DELAY_US", "100", 1);
-  for (int round = 0; round < 6; ++round) {
+  for (int round = 0; round < 10; ++round) {
     const int lossless = round & 1;
     youthSlamSetOptions(lossless, 4);
     initSlamModule(argv[1], NULL);
@@ -63,15 +80,17 @@ int main(int argc, char** argv) {
       return 1;
     }
     atomic_store(&g_quit, 0);
-    g_pace_us = round >= 2 ? 150 : 0; /* rounds 0, 1: stop under overload */
-    long pushed = 0;
-    pthread_t tp, tr;
+    g_pace_us = round >= 6 ? 400 : (round >= 2 ? 150 : 0); /* rounds 0, 1: stop under overload; two producers: each slower */
+    long pushed = 0, pushed2 = 0;
+    const int two = round >= 6; /* rounds 6..9: a zero-copy producer next to the copying one */
+    pthread_t tp, tp2, tr;
     pthread_create(&tp, NULL, producer, &pushed);
+    if (two) pthread_create(&tp2, NULL, producer_zero_copy, &pushed2);
     pthread_create(&tr, NULL, reader, NULL);
     usleep(20000);
     if (round >= 2) {
       youthSlamDrain();
-      if (round >= 4) {
+      if (round >= 4 && round != 6 && round != 7) {
         resetSlam();
         usleep(5000);
         if (!saveSlamMap(argv[2])) {
@@ -83,8 +102,9 @@ int main(int argc, char** argv) {
     stopSlamModule(); /* with the producer still pushing */
     atomic_store(&g_quit, 1);
     pthread_join(tp, NULL);
+    if (two) pthread_join(tp2, NULL);
     pthread_join(tr, NULL);
-    if (isSlamModuleRunning() || pushed <= 0) {
+    if (isSlamModuleRunning() || pushed <= 0 || (two && pushed2 <= 0)) {
       fprintf(stderr, "round %d: running=%d pushed=%ld\n", round, isSlamModuleRunning(), pushed);
       return 1;
     }

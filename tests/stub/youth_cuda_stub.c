@@ -138,7 +138,8 @@ int youth_cuda_get_trajectory(youth_cuda_handle* h, int stream, int first, int m
   if (n > max_frames) n = max_frames;
   if (poses_out) memcpy(poses_out, h->poses + 12 * (size_t)first, sizeof(float) * 12 * (size_t)n);
   if (timestamps_out) memcpy(timestamps_out, h->ts + first, sizeof(uint32_t) * (size_t)n);
-  if (status_out) memset(status_out, 0, sizeof(uint32_t) * (size_t)n);
+  if (status_out)
+    for (int i = 0; i < n; ++i) status_out[i] = first + i == 0 ? YOUTH_STATUS_FIRST : 0u;
   return n;
 }
 
@@ -158,6 +159,8 @@ int youth_cuda_read_last_inliers_async(youth_cuda_handle* h, int stream, int* in
 }
 
 int youth_cuda_last_inliers(youth_cuda_handle* h, int stream) { return h && stream == 0 ? 1000 + h->count : 0; }
+
+int youth_cuda_sync(youth_cuda_handle* h) { return h != NULL; }
 
 int youth_cuda_reset(youth_cuda_handle* h, int stream) {
   (void)stream;

@@ -44,6 +44,37 @@ def test_reference_arm_prints_the_contract_line():
     assert j["e2e"] == {"value": j["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
+def test_reference_arm_maps_none_of_the_gpu_libraries():
+    """the CPU arm must not load the product's CUDA code (nor the facade that links it): frames come from
+    libyouth_synth.so (plain C), the configuration from the oracle"""
+    code = ("import sys, bench; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0']; "
+            "bench.main(); maps = open('/proc/self/maps').read(); "
+            "sys.stderr.write('MAPPED:' + ','.join(sorted({l.split('/')[-1] for l in maps.splitlines() if '.so' in l and "
+            "('youth' in l or 'AlgorithmModule' in l or 'libcuda' in l)})) + '\\n')")
+    env = dict(os.environ)
+    env.pop("RANK", None)
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    mapped = [l for l in r.stderr.splitlines() if l.startswith("MAPPED:")][-1][len("MAPPED:"):].split(",")
+    assert "libyouth_synth.so" in mapped and any(m.startswith("libyouth_oracle") for m in mapped), mapped
+    assert not any(m.startswith(("libyouth_cuda", "libAlgorithmModule", "libcuda")) for m in mapped), mapped
+
+
+def test_both_arms_describe_the_same_configuration():
+    import bench
+
+    class A:
+        pass
+
+    a = A()
+    a.user_ppt, a.mode = 0, "frame"
+    ppt = bench.default_ppt(a, 300, 1)
+    ours = bench.config_dict(640, 480, 3, 1, 300, ppt, 1, "frame")
+    assert ppt == 128 and "host_placement" not in ours  # nothing arm-specific inside `config`
+    r = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0")
+    assert json.loads(r.stdout.strip())["config"] == ours
+
+
 def test_reference_arm_other_ranks_exit_quietly():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",

@@ -42,6 +42,9 @@ def fut(tmp_path_factory):
     L.youth_bin_write_frame.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.youth_bin_write_eof.argtypes = [C.c_void_p]
     L.stub_torn_frames.restype = C.c_long
+    L.youthSlamAcquireSlot.restype = C.c_void_p
+    L.youthSlamAcquireSlot.argtypes = [C.c_int, C.c_int]
+    L.youthSlamCommitSlot.argtypes = [C.c_uint32]
     cfg = tmp_path_factory.mktemp("cfg") / "cam.yaml"
     cfg.write_text(f"%YAML:1.0\nCamera.width: {W}\nCamera.height: {H}\nCamera.fx: 57.03\nCamera.fy: 57.03\n"
                    "Camera.cx: 32.0\nCamera.cy: 24.0\nDepthMapFactor: 1000.0\n")
@@ -124,6 +127,59 @@ def test_lossless_mode_tracks_every_frame_once_and_in_order(fut, tmp_path):
     assert fut.isSlamModuleRunning() == 0
 
 
+def test_zero_copy_producer_fills_ring_slots_in_place(fut, monkeypatch):
+    """youthSlamAcquireSlot / youthSlamCommitSlot (include/youth_slam_ext.h): the producer writes the frame into the
+    page-locked ring itself; mixed freely with processSlamFrame(), every frame is tracked once and in order; large
+    launch groups (the 64-frame cap is gone)."""
+    monkeypatch.setenv("YOUTH_STUB_DELAY_US", "300")  # a tracker slower than the producer: frames queue up into groups
+    fut.youthSlamSetOptions(1, 96)
+    fut.initSlamModule(fut.cfg_path, None)
+    assert fut.youthSlamCommitSlot(0) == 0  # nothing acquired
+    assert not fut.youthSlamAcquireSlot(W + 8, H)  # not the configured size
+    n = 400
+    for i in range(1, n + 1):
+        if i % 3 == 0:
+            f = frame(i)
+            assert fut.processSlamFrame(f.ctypes.data, None, W, H, 7 * i) == 1
+        else:
+            slot = fut.youthSlamAcquireSlot(W, H)
+            assert slot
+            view = np.ctypeslib.as_array((C.c_uint16 * (W * H)).from_address(slot)).reshape(H, W)
+            view[...] = frame(i)
+            assert fut.youthSlamCommitSlot(7 * i) == 1
+    fut.youthSlamDrain()
+    assert stats(fut) == (n, 0, n)
+    poses, ts = trajectory(fut, n)
+    assert list(poses[:, 3]) == list(range(1, n + 1)) and list(ts) == [7 * i for i in range(1, n + 1)]
+    assert poses[:, 11].max() > 64  # launch groups larger than the old cap did form
+    assert fut.stub_torn_frames() == 0
+    fut.stopSlamModule()
+    assert not fut.youthSlamAcquireSlot(W, H)  # stopped
+
+
+def test_tracker_failure_is_sticky_until_reset(fut, monkeypatch):
+    """once the tracker refuses a run (here: trajectory capacity exhausted) processSlamFrame reports failure
+    instead of accepting frames that can never be tracked; resetSlam() clears it"""
+    monkeypatch.setenv("YOUTH_SLAM_TRAJ_CAPACITY", "10")
+    fut.youthSlamSetOptions(1, 4)
+    fut.initSlamModule(fut.cfg_path, None)
+    results = []
+    for i in range(1, 60):
+        f = frame(i)  # keep the array alive across the call
+        results.append(fut.processSlamFrame(f.ctypes.data, None, W, H, i))
+    fut.youthSlamDrain()
+    assert results[0] == 1 and results[-1] == 0  # the failure reached the producer
+    f1 = frame(1)
+    assert fut.processSlamFrame(f1.ctypes.data, None, W, H, 0) == 0
+    a, d, t = stats(fut)
+    assert t <= 10
+    fut.resetSlam()
+    assert fut.processSlamFrame(f1.ctypes.data, None, W, H, 0) == 1
+    fut.youthSlamDrain()
+    assert len(trajectory(fut, 20)[0]) == 1
+    fut.stopSlamModule()
+
+
 def test_default_back_pressure_drops_the_oldest_frames(fut, monkeypatch):
     """SLAM.cpp:158-169: the producer never blocks; more than 10 waiting -> the oldest are dropped down to 5."""
     monkeypatch.setenv("YOUTH_STUB_DELAY_US", "3000")  # a tracker much slower than the producer
@@ -132,7 +188,8 @@ def test_default_back_pressure_drops_the_oldest_frames(fut, monkeypatch):
     n = 120
     t0 = time.time()
     for i in range(1, n + 1):
-        assert fut.processSlamFrame(frame(i).ctypes.data, None, W, H, i) == 1
+        f = frame(i)  # keep the array alive across the call
+        assert fut.processSlamFrame(f.ctypes.data, None, W, H, i) == 1
     produced_in = time.time() - t0
     fut.youthSlamDrain()
     accepted, dropped, tracked = stats(fut)

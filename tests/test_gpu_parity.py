@@ -368,6 +368,57 @@ def test_two_groups_in_flight_give_the_blocking_results(pkg, small_seq):
     trk.close()
 
 
+def test_many_streams_two_steps_in_flight_wait_really_waits(pkg):
+    """16 sequences in one handle, one asynchronous read-back per sequence and step, two steps in flight: 32 tickets
+    are issued between a ticket and its wait, and a step's buffers are only read after its LAST ticket was waited
+    for.  Regression test: with 16 event slots the wait on a recycled slot used to return without synchronising.
+    Also waits on a ticket that is several hundred reads old (its slot was re-used many times)."""
+    import ctypes as C
+
+    from slam_rgbd_b200 import binding as B
+
+    S, n, w, h = 16, 3, 160, 120
+    small = dict(width=w, height=h, fx=570.3 / 4, fy=570.3 / 4, cx=80.0, cy=60.0)
+    seqs = [pkg.synth_sequence(n, w, h, sequence=s) for s in range(S)]
+    trk = make_tracker(pkg, batch=n, n_streams=S, traj_capacity=n, **small)
+    ref = [p.copy() for p in trk.track_batch(seqs)]
+    pins = []
+    for s in range(S):
+        pin = trk.lib.youth_cuda_host_alloc(seqs[s].nbytes)
+        C.memmove(pin, seqs[s].ctypes.data, seqs[s].nbytes)
+        pins.append(pin)
+    res = [[trk.lib.youth_cuda_host_alloc(n * 48) for _ in range(S)] for _ in range(2)]
+    views = [[np.ctypeslib.as_array((C.c_float * (n * 12)).from_address(p)).reshape(n, 12) for p in r] for r in res]
+    pending, first_ticket = [], None
+    for i in range(12):
+        trk.reset()
+        trk.track_batch_ptrs(pins, n, B.MEM_HOST_PINNED)
+        tickets = []
+        for s in range(S):
+            views[i % 2][s][...] = -1.0
+            got, t = trk.read_trajectory_async(res[i % 2][s], n, stream=s)
+            assert got == n
+            tickets.append(t)
+        if first_ticket is None:
+            first_ticket = tickets[0]
+        pending.append((i, tickets))
+        if len(pending) > 1:
+            j, ts = pending.pop(0)
+            trk.wait_ticket(ts[-1])  # 2 * S - 1 newer tickets exist by now
+            for s in range(S):
+                assert np.array_equal(views[j % 2][s].view(np.uint32), ref[s].view(np.uint32)), f"step {j} sequence {s}"
+    j, ts = pending.pop(0)
+    trk.wait_ticket(ts[-1])
+    for s in range(S):
+        assert np.array_equal(views[j % 2][s].view(np.uint32), ref[s].view(np.uint32))
+    trk.wait_ticket(first_ticket)  # 191 reads old
+    with pytest.raises(Exception):
+        trk.wait_ticket(ts[-1] + 1)  # never issued
+    for p in pins + res[0] + res[1]:
+        trk.lib.youth_cuda_host_free(p)
+    trk.close()
+
+
 @pytest.mark.parametrize("fused", ["1", "0"])
 @pytest.mark.parametrize("iters", [(10, 5, 4), (3, 0, 2), (0, 0, 3)])
 def test_fused_and_per_iteration_icp_match_the_oracle(pkg, oracle, small_seq, fused, iters, monkeypatch):
