@@ -160,7 +160,13 @@ void* youth_cuda_host_alloc(size_t bytes);
 void youth_cuda_host_free(void* p);
 
 /* Parity hooks.  `frame` is the absolute frame index inside the sequence; it must still
- * be resident in the ring (the last cfg.batch+1 frames are). */
+ * be resident in the ring (the last cfg.batch+1 frames are).
+ * YOUTH_DBG_DEPTH and YOUTH_DBG_PYRCNT read the filtered float depth pyramid and the pyramid sample counts, which
+ * nothing on the product path consumes: the tracker only stores them (and only allocates their buffers) after
+ * youth_cuda_debug_enable_maps(), to be called before the frames of interest are tracked (YOUTH_DEBUG_MAPS=1 in
+ * the environment does the same at init; frame-to-model tracking enables them itself, its ray cast starts from
+ * the depth pyramid).  Vertex / normal maps and masks are always readable. */
+int youth_cuda_debug_enable_maps(youth_cuda_handle* h);
 int youth_cuda_debug_read(youth_cuda_handle* h, int what, int stream, int frame, int level,
                           void* dst, size_t dst_bytes);
 /* One association + reduction pass (stage 3+4) of frame `frame` against frame-1 at `level`

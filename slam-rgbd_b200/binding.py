@@ -133,6 +133,7 @@ def cuda_lib():
         "youth_cuda_trajectory_device_ptr": (C.c_void_p, [H, C.c_int]),
         "youth_cuda_host_alloc": (C.c_void_p, [C.c_size_t]),
         "youth_cuda_host_free": (None, [C.c_void_p]),
+        "youth_cuda_debug_enable_maps": (C.c_int, [H]),
         "youth_cuda_debug_read": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
         "youth_cuda_debug_icp": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
         "youth_cuda_debug_rcp_check": (C.c_longlong, [H, C.c_uint32, C.c_uint32]),
@@ -373,6 +374,10 @@ class Tracker:
 
     def last_inliers(self, stream=0):
         return self.lib.youth_cuda_last_inliers(self.h, stream)
+
+    def enable_debug_maps(self):
+        """store the float depth pyramid / pyramid sample counts too (DBG_DEPTH, DBG_PYRCNT); call before tracking"""
+        self._check(self.lib.youth_cuda_debug_enable_maps(self.h), "youth_cuda_debug_enable_maps")
 
     def debug_read(self, what, frame, level, stream=0):
         h, w = self.level_shape(level)

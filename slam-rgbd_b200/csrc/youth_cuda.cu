@@ -1,6 +1,6 @@
 /*
  * youth_cuda.cu -- libyouth_cuda.so: the C ABI declared in include/youth_cuda.h over the
- * sm_100a kernels in youth_kernels.cuh.  No CPU fallback: every compute entry point
+ * sm_100a kernels in youth_ingest.cu, youth_icp.cu, youth_model.cuh and youth_codec.cuh.  No CPU fallback: every compute entry point
  * fails (returns 0, youth_cuda_last_error() says why) when no CUDA device is usable.
  *
  * Device-resident state per handle (all in HBM, sized at init, nothing allocated per frame):
@@ -21,7 +21,7 @@
 
 #include "youth_cuda.h"
 #include "youth_codec.h"
-#include "youth_kernels.cuh"
+#include "youth_common.cuh"
 #include "youth_model.cuh"
 
 #define YK_CHUNK_FRAMES 16 /* host-fed groups are copied + preprocessed in chunks of at least this many frames */
@@ -84,10 +84,12 @@ struct youth_cuda_handle {
   float ws[49];
   float* wr;
   float* wt; /* product table of the bilateral (IngestParams.wt) */
-  /* YK_FAST_DIV builds: reciprocal form of the vertex divisions, used when the exhaustive device check passed */
+  /* reciprocal form of the vertex divisions (div_cfg), used when the exhaustive device check at init passed */
   int fast_div;
   float r_df, r_fx[YOUTH_MAX_LEVELS], r_fy[YOUTH_MAX_LEVELS];
-  int icp_xy; /* YK_ICP_XY builds: k_icp recomputes vx, vy (fast_div holds and the multiply-high pixel quotient is exact) */
+  /* the float depth pyramid and the pyramid sample counts are only stored (and their buffers only exist) for the
+   * parity read-back and for the model ray cast's depth hint: youth_cuda_debug_enable_maps / youth_cuda_enable_model */
+  bool debug_maps;
   int range_cut;
   cudaEvent_t ticket_ev[YK_TICKETS]; /* youth_cuda_read_trajectory_async / youth_cuda_wait_ticket */
   uint64_t ticket_next;
@@ -311,6 +313,35 @@ extern "C" void youth_cuda_destroy(youth_cuda_handle* h) {
   delete h;
 }
 
+/* buffers + kernel instantiation for the float depth pyramid and the pyramid sample counts (parity read-back, model
+ * ray-cast hint).  Cached graphs were captured with the instantiation that does not store them: drop them. */
+static int ensure_debug_maps(youth_cuda_handle* h) {
+  if (h->debug_maps) return 1;
+  const size_t slots = (size_t)h->S * h->R;
+  for (int l = 0; l < h->cfg.levels; ++l) {
+    CU(dalloc(&h->depth[l], slots * h->npix[l]));
+    CU(dalloc(&h->pyrcnt[l], slots * h->npix[l]));
+  }
+  for (int g2 = 0; g2 < YK_GRAPH_SLOTS; ++g2)
+    if (h->graphs[g2].exec) {
+      cudaGraphExecDestroy(h->graphs[g2].exec);
+      h->graphs[g2].exec = NULL;
+    }
+  if (h->m.graph) {
+    cudaGraphExecDestroy(h->m.graph);
+    h->m.graph = NULL;
+  }
+  h->debug_maps = true;
+  return 1;
+}
+
+extern "C" int youth_cuda_debug_enable_maps(youth_cuda_handle* h) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  return ensure_debug_maps(h);
+}
+
 static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -374,9 +405,7 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
   h->icp_nq = 1;
   const size_t slots = (size_t)h->S * h->R;
   for (int l = 0; l < cfg->levels; ++l) {
-    CU(dalloc(&h->depth[l], slots * h->npix[l]));
     CU(dalloc(&h->maps[l], slots * 3 * h->npix[l]));
-    CU(dalloc(&h->pyrcnt[l], slots * h->npix[l]));
   }
   const size_t frame_px = (size_t)cfg->width * cfg->height;
   for (int k = 0; k < 2; ++k) {
@@ -413,10 +442,11 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
     }
   }
   h->fast_div = 0;
-#if YK_FAST_DIV
   {
-    /* The dividends of the vertex divisions are d in [1, 65535], and (u - c) * z with z = d / depth_factor:
-     * with the bounds below they are 0 or lie in [2^-53, 2^51], inside the range k_div_check covers. */
+    /* The divisions of the back-projection by depth_factor, fx, fy (viewerModule.c:343-345) in the reciprocal form
+     * div_cfg, when the device confirms -- exhaustively, here -- that it gives the IEEE quotient for every dividend
+     * that can occur: d in [1, 65535], and (u - c) * z with z = d / depth_factor; with the bounds below they are 0
+     * or lie in [2^-53, 2^51], inside the range k_div_check covers.  YOUTH_NO_FAST_DIV=1 keeps the divisions. */
     const float df = cfg->depth_factor;
     bool ok = df >= 0x1p-20f && df <= 0x1p20f && !getenv("YOUTH_NO_FAST_DIV");
     unsigned long long* d_bad = NULL;
@@ -424,8 +454,8 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
     CU(cudaMalloc((void**)&d_bad, sizeof(bad)));
     CU(cudaMemset(d_bad, 0, sizeof(bad)));
     h->r_df = 1.0f / df;
-    if (ok) k_div_check<<<148 * 8, 256>>>(df, h->r_df, d_bad);
-    for (int l = 0; l < cfg->levels && ok; ++l) {
+    if (ok) yk_launch_div_check(df, h->r_df, d_bad);
+    for (int l = 0; l < cfg->levels; ++l) {
       const LevelGeom& g = h->lv[l];
       ok = ok && g.fx >= 0x1p-10f && g.fx <= 0x1p20f && g.fy >= 0x1p-10f && g.fy <= 0x1p20f &&
            (g.cx == 0.0f || (fabsf(g.cx) >= 0x1p-10f && fabsf(g.cx) <= 0x1p20f)) &&
@@ -433,8 +463,8 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
       h->r_fx[l] = 1.0f / g.fx;
       h->r_fy[l] = 1.0f / g.fy;
       if (ok) {
-        k_div_check<<<148 * 8, 256>>>(g.fx, h->r_fx[l], d_bad);
-        k_div_check<<<148 * 8, 256>>>(g.fy, h->r_fy[l], d_bad);
+        yk_launch_div_check(g.fx, h->r_fx[l], d_bad);
+        yk_launch_div_check(g.fy, h->r_fy[l], d_bad);
       }
     }
     CU(cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost));
@@ -442,17 +472,11 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
     CU(cudaGetLastError());
     h->fast_div = ok && bad == 0 ? 1 : 0;
   }
-#endif
-  h->icp_xy = 0;
-#if YK_ICP_XY
+  h->debug_maps = false;
   {
-    /* p / w == umulhi(p, ceil(2^32 / w)) for every p < npix when npix * w <= 2^32 */
-    bool ok = h->fast_div && !getenv("YOUTH_NO_ICP_XY");
-    for (int l = 0; l < cfg->levels; ++l)
-      ok = ok && h->lv[l].w >= 2 && (unsigned long long)h->npix[l] * (unsigned long long)h->lv[l].w <= (1ull << 32);
-    h->icp_xy = ok ? 1 : 0;
+    const char* e = getenv("YOUTH_DEBUG_MAPS");
+    if (e && *e == '1' && !ensure_debug_maps(h)) return 0;
   }
-#endif
   CU(dalloc(&h->pose_d, (size_t)h->P * 12));
   CU(dalloc(&h->pose_f, (size_t)h->P * 12));
   CU(dalloc(&h->partials, (size_t)h->P * h->max_runs * 32));
@@ -466,7 +490,7 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
     const char* fc = getenv("YOUTH_ICP_FUSED_COOP");
     h->fused_coop = !(fc && *fc == '0');
     int per_sm = 0, sms = 0, coop = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_fused, 32 * YK_ICP_WARPS, 0));
+    CU(yk_icp_fused_ctas_per_sm(&per_sm));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device));
     CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device));
     h->fused_max_ctas = per_sm * sms;
@@ -566,19 +590,7 @@ static void launch_icp_on(youth_cuda_handle* h, const IcpParams& ip, int fn, int
   /* grid = (CTAs of a pair, frames of the range, sequences): the kernel reads its pair off blockIdx without a
    * division (the division's live range cost k_icp eight spill instructions per two pixels) */
   const dim3 grid((h->nruns[level] + YK_ICP_WARPS - 1) / YK_ICP_WARPS, fn, h->S);
-#if YK_ICP_XY
-  if (h->icp_xy && ip.model == nullptr) { /* the previous frame's maps come from stage 2: vx, vy can be recomputed */
-    if ((long long)grid.x * fn * h->S <= YK_ICP_LAST_CTA_MAX_CTAS)
-      k_icp<false, true, YK_ICP_XY><<<grid, 32 * YK_ICP_WARPS, 0, q>>>(ip);
-    else
-      k_icp<false, false, YK_ICP_XY><<<grid, 32 * YK_ICP_WARPS, 0, q>>>(ip);
-    return;
-  }
-#endif
-  if ((long long)grid.x * fn * h->S <= YK_ICP_LAST_CTA_MAX_CTAS)
-    k_icp<false, true><<<grid, 32 * YK_ICP_WARPS, 0, q>>>(ip);
-  else
-    k_icp<false, false><<<grid, 32 * YK_ICP_WARPS, 0, q>>>(ip);
+  yk_launch_icp((long long)grid.x * fn * h->S <= YK_ICP_LAST_CTA_MAX_CTAS, grid, q, ip);
 }
 
 /* grid of one k_icp_fused launch over fn frames of every sequence, 0 when the fused kernel does not apply:
@@ -631,21 +643,12 @@ static int launch_icp_fused(youth_cuda_handle* h, const RingGeom& ring, int gx, 
   fp.pair_status = h->pair_status;
   fp.min_inliers = c.min_inliers;
   fp.f0 = f0;
-  cudaLaunchConfig_t lc;
-  memset(&lc, 0, sizeof(lc));
-  lc.gridDim = dim3(gx, fn, h->S);
-  lc.blockDim = dim3(32 * YK_ICP_WARPS);
-  lc.stream = q;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeCooperative; /* every CTA resident at once, or the launch waits its turn */
-  at[0].val.cooperative = 1;
-  lc.attrs = at;
-  lc.numAttrs = h->fused_coop ? 1 : 0;
+  bool coop = h->fused_coop;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   CU(cudaStreamIsCapturing(q, &cap));
-  if (cap != cudaStreamCaptureStatusNone) lc.numAttrs = 0; /* graph nodes: plain launch, see fused_grid_x */
+  if (cap != cudaStreamCaptureStatusNone) coop = false; /* graph nodes: plain launch, see fused_grid_x */
   h->launches++;
-  CU(cudaLaunchKernelEx(&lc, k_icp_fused, fp));
+  CU(yk_launch_icp_fused(dim3(gx, fn, h->S), q, coop, fp));
   return 1;
 }
 
@@ -678,11 +681,6 @@ static IcpParams icp_params(const youth_cuda_handle* h, int level, const RingGeo
   ip.model = h->m.on ? h->m.maps[level] : NULL;
   ip.f0 = 0;
   ip.fn = ring.n;
-#if YK_ICP_XY
-  ip.r_fx = h->r_fx[level];
-  ip.r_fy = h->r_fy[level];
-  ip.w_magic = (unsigned int)(((1ull << 32) + (unsigned long long)h->lv[level].w - 1) / (unsigned long long)h->lv[level].w);
-#endif
   return ip;
 }
 
@@ -719,33 +717,17 @@ static int enqueue_preprocess(youth_cuda_handle* h, const uint16_t* const* raw_d
     ip.wr = h->wr;
     ip.depth_factor = c.depth_factor;
     ip.pyr_thr = 3.0f * c.sigma_range_mm;
-    dim3 grid((c.width + YK_TILE_W - 1) / YK_TILE_W, (c.height + YK_TILE_H - 1) / YK_TILE_H, frames);
+    dim3 grid((c.width + 63) / 64, (c.height + 15) / 16, frames); /* 64 x 16 pixel tiles (youth_ingest.cu) */
     ProfScope ps(h, YOUTH_PROF_INGEST);
     ip.wt = reinterpret_cast<const float4*>(h->wt);
-#if YK_FAST_DIV
-    ip.fast_div = h->fast_div;
     ip.r_df = h->r_df;
     for (int l = 0; l < c.levels; ++l) {
       ip.r_fx[l] = h->r_fx[l];
       ip.r_fy[l] = h->r_fy[l];
     }
-#endif
-#if YK_FAST_DIV
-    if (h->fast_div) {
-      if (!c.bilateral)
-        k_ingest<YK_INGEST_RAW, true><<<grid, 256, 0, h->stream>>>(ip);
-      else if (h->range_cut + 2 <= YK_WT_STRIDE && !h->ingest_generic)
-        k_ingest<YK_INGEST_BILATERAL_WT, true><<<grid, 256, 0, h->stream>>>(ip);
-      else
-        k_ingest<YK_INGEST_BILATERAL, true><<<grid, 256, 0, h->stream>>>(ip);
-    } else
-#endif
-    if (!c.bilateral)
-      k_ingest<YK_INGEST_RAW><<<grid, 256, 0, h->stream>>>(ip);
-    else if (h->range_cut + 2 <= YK_WT_STRIDE && !h->ingest_generic)
-      k_ingest<YK_INGEST_BILATERAL_WT><<<grid, 256, 0, h->stream>>>(ip);
-    else
-      k_ingest<YK_INGEST_BILATERAL><<<grid, 256, 0, h->stream>>>(ip);
+    const int mode = !c.bilateral ? YK_INGEST_RAW
+                                  : (h->range_cut + 2 <= YK_WT_STRIDE && !h->ingest_generic ? YK_INGEST_BILATERAL_WT : YK_INGEST_BILATERAL);
+    yk_launch_ingest(mode, h->fast_div != 0, h->debug_maps, grid, h->stream, ip);
   }
   /* stage 2b */
   {
@@ -765,7 +747,7 @@ static int enqueue_preprocess(youth_cuda_handle* h, const uint16_t* const* raw_d
     if (total > 0) {
       dim3 grid((total + 255) / 256, frames);
       ProfScope ps(h, YOUTH_PROF_NORMALS);
-      k_normals<<<grid, 256, 0, h->stream>>>(np);
+      yk_launch_normals(h->fast_div != 0, grid, h->stream, np);
     }
   }
   CU(cudaGetLastError());
@@ -885,7 +867,7 @@ static int enqueue_compose(youth_cuda_handle* h, int n) {
   cp.last_status = h->m.on ? h->m.last_status : NULL;
   {
     ProfScope ps(h, YOUTH_PROF_MISC);
-    k_compose<<<h->S, 128, 0, h->stream>>>(cp);
+    yk_launch_compose(h->S, h->stream, cp);
   }
   CU(cudaGetLastError());
   return 1;
@@ -941,6 +923,7 @@ extern "C" int youth_cuda_enable_model(youth_cuda_handle* h, const youth_tsdf_co
   if (t->max_weight < 1 || t->max_weight > 32767) return fail("max_weight must be 1..32767");
   if (!(t->near_m > 0.f) || !(t->far_m > t->near_m)) return fail("need 0 < near_m < far_m");
   CU(cudaSetDevice(h->cfg.device));
+  if (!ensure_debug_maps(h)) return 0; /* the ray cast starts its march from the fused frame's depth pyramid */
   h->m.cfg = *t;
   TsdfGeom& g = h->m.geom;
   g.dx = t->dim[0];
@@ -1032,7 +1015,7 @@ static int enqueue_raycast(youth_cuda_handle* h, int s0, int ns, int hint_slot) 
     np.levels = h->cfg.levels;
     const dim3 ngrid((px + 255) / 256, (unsigned)ns);
     ProfScope ps(h, YOUTH_PROF_RAYCAST);
-    k_normals<<<ngrid, 256, 0, h->stream>>>(np);
+    yk_launch_normals(h->fast_div != 0, ngrid, h->stream, np);
   }
   CU(cudaGetLastError());
   return 1;
@@ -1587,6 +1570,7 @@ extern "C" int youth_cuda_debug_read(youth_cuda_handle* h, int what, int stream,
   const size_t off = ((size_t)stream * h->R + slot) * np;
   switch (what) {
     case YOUTH_DBG_DEPTH:
+      if (!h->debug_maps) return fail("the depth pyramid is only stored after youth_cuda_debug_enable_maps (call it before tracking)");
       if (dst_bytes < np * 4) return fail("dst too small");
       CU(cudaMemcpy(dst, h->depth[level] + off, np * 4, cudaMemcpyDeviceToHost));
       return 1;
@@ -1596,6 +1580,7 @@ extern "C" int youth_cuda_debug_read(youth_cuda_handle* h, int what, int stream,
       return read_planes(h->maps[level] + ((size_t)stream * h->R + slot) * 3 * np, np, what, dst, dst_bytes);
     }
     case YOUTH_DBG_PYRCNT:
+      if (!h->debug_maps) return fail("the pyramid sample counts are only stored after youth_cuda_debug_enable_maps (call it before tracking)");
       if (dst_bytes < np) return fail("dst too small");
       CU(cudaMemcpy(dst, h->pyrcnt[level] + off, np, cudaMemcpyDeviceToHost));
       return 1;
@@ -1618,7 +1603,7 @@ extern "C" long long youth_cuda_debug_rcp_check(youth_cuda_handle* h, uint32_t l
   unsigned long long bad = 0;
   if (cudaMalloc((void**)&d, sizeof(bad)) != cudaSuccess) return -1;
   cudaMemsetAsync(d, 0, sizeof(bad), h->stream);
-  k_rcp_check<<<148 * 8, 256, 0, h->stream>>>(lo_bits, hi_bits, d);
+  yk_launch_rcp_check(h->stream, lo_bits, hi_bits, d);
   h->launches++;
   cudaMemcpyAsync(&bad, d, sizeof(bad), cudaMemcpyDeviceToHost, h->stream);
   const cudaError_t e = cudaStreamSynchronize(h->stream);
@@ -1651,7 +1636,7 @@ extern "C" int youth_cuda_debug_icp(youth_cuda_handle* h, int stream, int frame,
   {
     ProfScope ps(h, YOUTH_PROF_ICP0 + level);
     const dim3 grid((h->nruns[level] + YK_ICP_WARPS - 1) / YK_ICP_WARPS, 1);
-    k_icp<true, false><<<grid, 32 * YK_ICP_WARPS, 0, h->stream>>>(ip);
+    yk_launch_icp_debug(grid, h->stream, ip);
   }
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(sums_out, h->sums, sizeof(double) * 32, cudaMemcpyDeviceToHost, h->stream));

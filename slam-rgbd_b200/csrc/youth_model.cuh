@@ -15,7 +15,7 @@
  *                     vertex map: k_normals (stage 2b) runs over the model maps right after.
  *   k_fill_u32        volume reset
  *
- * Same arithmetic contract as youth_kernels.cuh (--fmad=false, explicit fma where specified,
+ * Same arithmetic contract as youth_common.cuh (--fmad=false, explicit fma where specified,
  * IEEE division / sqrt); bit-identical to the CPU statement.  HBM/L2-bound gather work: no
  * tensor cores.
  */
@@ -23,7 +23,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "youth_kernels.cuh"
+#include "youth_common.cuh"
 #include "youth_model.h"
 
 #define YM_SCALE 32767.0f

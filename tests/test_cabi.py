@@ -152,17 +152,6 @@ def test_init_rejects_bad_configs(pkg):
             Tracker(pkg.default_config(**kw))
 
 
-def test_icp_xy_pixel_quotient_is_exact():
-    """-DYK_ICP_XY: k_icp gets the row of pixel p as umulhi(p, ceil(2^32 / w)); the host enables it when
-    npix * w <= 2^32 (youth_cuda.cu, init_impl).  Exhaustive over every level of the configurations in use."""
-    for w, h in ((640, 480), (320, 240), (160, 120), (80, 60), (1280, 960), (2047, 1024), (2, 2), (6, 4)):
-        assert w * h * w <= 1 << 32
-        magic = ((1 << 32) + w - 1) // w
-        assert magic < 1 << 32
-        p = np.arange(w * h, dtype=np.uint64)
-        assert np.array_equal((p * np.uint64(magic)) >> np.uint64(32), p // np.uint64(w))
-
-
 def test_product_never_references_the_oracle():
     """the oracle is test infrastructure: nothing under slam-rgbd_b200/ or include/ may
     include, link or import it."""

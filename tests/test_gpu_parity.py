@@ -45,6 +45,9 @@ def test_preprocess_parity(pkg, oracle, small_seq, bilateral):
 
     frames, _ = small_seq
     trk = make_tracker(pkg, bilateral=bilateral, batch=4)
+    with pytest.raises(Exception):
+        trk.debug_read(B.DBG_DEPTH, 0, 0)  # nothing tracked yet
+    trk.enable_debug_maps()  # the product instantiation does not store the float depth pyramid / sample counts
     ocfg = oracle.config_from(trk.cfg)
     trk.track_batch([frames[:3]])
     for fi in range(3):
@@ -224,8 +227,16 @@ def test_parity_across_configurations(pkg, oracle, w, h, levels, extra, noise):
     assert np.array_equal(st, st_o)
     assert np.array_equal(poses.view(np.uint32), want.view(np.uint32))
     of = oracle.OFrame(ocfg, frames[2])
+    with pytest.raises(Exception):  # the product path does not store the depth pyramid: the read-back refuses
+        trk.debug_read(B.DBG_DEPTH, 2, 0)
+    dbg = make_tracker(pkg, **base)
+    dbg.enable_debug_maps()
+    assert np.array_equal(dbg.track_batch([frames])[0].view(np.uint32), want.view(np.uint32))
     for level in range(levels):
-        assert np.array_equal(trk.debug_read(B.DBG_DEPTH, 2, level), of.depth(level))
+        assert np.array_equal(dbg.debug_read(B.DBG_DEPTH, 2, level), of.depth(level))
+        assert np.array_equal(dbg.debug_read(B.DBG_VERTEX, 2, level).view(np.uint32), of.vmap(level).view(np.uint32))
+    dbg.close()
+    for level in range(levels):
         assert np.array_equal(trk.debug_read(B.DBG_MASK, 2, level), of.mask(level))
         assert np.array_equal(trk.debug_read(B.DBG_VERTEX, 2, level).view(np.uint32), of.vmap(level).view(np.uint32))
         assert np.array_equal(trk.debug_read(B.DBG_NORMAL, 2, level).view(np.uint32), of.nmap(level).view(np.uint32))
@@ -316,6 +327,7 @@ def test_bilateral_table_and_generic_paths_match_the_oracle(pkg, oracle, small_s
     for forced in ("0", "1"):
         monkeypatch.setenv("YOUTH_INGEST_GENERIC", forced)
         trk = make_tracker(pkg, batch=2, sigma_range_mm=sigma_range_mm)
+        trk.enable_debug_maps()
         ocfg = oracle.config_from(trk.cfg)
         trk.track_batch([frames[:2]])
         of = oracle.OFrame(ocfg, frames[1])
@@ -366,6 +378,38 @@ def test_two_groups_in_flight_give_the_blocking_results(pkg, small_seq):
     for p in res + [pin]:
         trk.lib.youth_cuda_host_free(p)
     trk.close()
+
+
+def test_reciprocal_form_divisions_do_not_change_a_bit(pkg, oracle, small_seq, monkeypatch):
+    """The back-projection divides by depth_factor, fx, fy (viewerModule.c:343-345).  The device uses a host-side
+    reciprocal and two fused multiply-adds (div_cfg) after checking at init, exhaustively, that this gives the IEEE
+    quotient for the configured divisors; YOUTH_NO_FAST_DIV=1 keeps the divisions.  Both must give the oracle's maps
+    and poses bit for bit (also for a non-default depth scale and odd intrinsics)."""
+    from slam_rgbd_b200 import binding as B
+
+    frames, _ = small_seq
+    for extra in ({}, dict(depth_factor=5000.0, fx=525.0, fy=531.7, cx=319.5, cy=239.5)):
+        fr = frames if not extra else (frames.astype(np.uint32) * 5).astype(np.uint16)
+        got = {}
+        for no_fast in ("0", "1"):
+            if no_fast == "1":
+                monkeypatch.setenv("YOUTH_NO_FAST_DIV", "1")
+            else:
+                monkeypatch.delenv("YOUTH_NO_FAST_DIV", raising=False)
+            trk = make_tracker(pkg, batch=6, **extra)
+            poses = trk.track_batch([fr])[0]
+            maps = [trk.debug_read(what, 5, level) for level in range(3) for what in (B.DBG_VERTEX, B.DBG_NORMAL)]
+            got[no_fast] = (poses, maps)
+            ocfg = oracle.config_from(trk.cfg)
+            trk.close()
+        want, _, _ = oracle.track_sequence(ocfg, fr)
+        of = oracle.OFrame(ocfg, fr[5])
+        for no_fast in ("0", "1"):
+            poses, maps = got[no_fast]
+            assert np.array_equal(poses.view(np.uint32), want.view(np.uint32)), (extra, no_fast)
+            for level in range(3):
+                assert np.array_equal(maps[2 * level].view(np.uint32), of.vmap(level).view(np.uint32)), (extra, no_fast, level)
+                assert np.array_equal(maps[2 * level + 1].view(np.uint32), of.nmap(level).view(np.uint32)), (extra, no_fast, level)
 
 
 def test_many_streams_two_steps_in_flight_wait_really_waits(pkg):

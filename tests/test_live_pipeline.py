@@ -167,8 +167,6 @@ def test_sensor_to_logging_to_algorithm_drop_in(pkg, small_seq, ref):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("YOUTH_TEST_MQ_MODE") != "1",
-                    reason="opt-in until its first run on a GPU box (written after the round's last GPU minute): YOUTH_TEST_MQ_MODE=1")
 def test_playback_to_algorithm_module_on_the_viewer_queue(pkg, small_seq, ref, tmp_path):
     """Recording -> the reference's own startPlayback / playbackThread -> /logger_viewer_queue ->
     algorithmModule("mq:/logger_viewer_queue") -> tracker: the TUM trajectory equals direct tracking of the frames."""

@@ -581,3 +581,44 @@ def test_golden_fixture(oracle):
         assert sha(cur.depth(level)) == str(g[f"depth_sha_l{level}"])
         assert sha(cur.vmap(level)) == str(g[f"vmap_sha_l{level}"])
         assert sha(cur.nmap(level)) == str(g[f"nmap_sha_l{level}"])
+
+
+def test_pose_agrees_with_an_order_independent_float64_icp(oracle):
+    """The oracle's reduction order is the kernel's geometry (icp_ppt, lane -> run -> chain), so oracle == device bit
+    for bit says nothing about whether that order matters.  Outside anchor: tests/numpy_icp.py solves the same
+    pairs in float64 with order-free numpy sums, numpy.linalg.solve and a libm SE(3) exponential.  The oracle's
+    relative poses must agree within the north-star tolerance (1e-4 m, 1e-4 rad) at BOTH reduction geometries
+    the build uses (icp_ppt 64 and 128), with and without sensor noise."""
+    import youth_pkg
+
+    import numpy_icp as NI
+
+    pkg = youth_pkg.load()
+    for noise in (0, 1):
+        frames = pkg.synth_sequence(4, noise=noise, first=40)
+        for ppt in (64, 128):
+            cfg = oracle.default_config(icp_ppt=ppt)
+            ofr = [oracle.OFrame(cfg, f) for f in frames]
+            geom = []
+            for l in range(cfg.levels):
+                g = oracle.level_geometry(cfg, l)
+                geom.append((g.w, g.h, g.fx, g.fy, g.cx, g.cy))
+            for i in range(1, len(frames)):
+                rel, st, inl = oracle.track_pair(cfg, ofr[i], ofr[i - 1])
+                maps = lambda fr: [(fr.vmap(l), fr.nmap(l)) for l in range(cfg.levels)]
+                T, inl64 = NI.icp_pair(cfg.levels, list(cfg.iters), geom, maps(ofr[i]), maps(ofr[i - 1]),
+                                       cfg.dist_thresh_m, cfg.cos_thresh, cfg.min_inliers)
+                R = rel.reshape(3, 4)
+                assert st == 0
+                assert np.linalg.norm(R[:, 3] - T[:3, 3]) < 1e-4, (noise, ppt, i)
+                assert NI.rot_angle(R[:, :3], T[:3, :3]) < 1e-4, (noise, ppt, i)
+                assert abs(inl - inl64) <= max(50, inl // 500)  # threshold ties may fall either way in double
+
+
+def test_pair_parallel_tracking_equals_the_serial_tracker(oracle, small_seq):
+    frames, _ = small_seq
+    cfg = oracle.default_config(icp_ppt=128)
+    a, sa, _ = oracle.track_sequence(cfg, frames)
+    b, sb, inl, _ = oracle.track_sequence_parallel(cfg, frames, threads=4)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(sa, sb)
+    assert inl[0] == 0 and inl[1:].min() > 100000

@@ -1,10 +1,10 @@
 #!/usr/bin/env python
-"""Quick A/B of A/B builds of libyouth_cuda.so (slam-rgbd_b200/lib/variants/, `make next-variants`) on a GPU box,
+"""Quick A/B of builds of libyouth_cuda.so (slam-rgbd_b200/lib/variants/, `make -C slam-rgbd_b200 variant NAME=.. EXTRA_NVFLAGS=..`) on a GPU box,
 without torch: for the default library and each variant, in its own process, track the same 300-frame synthetic
 sequence from page-locked host memory (one launch group, icp_ppt 128 = what bench.py runs), print the SHA-1 of the
 trajectory (bit-exactness against the default library is the gate) and the per-kernel-class CUDA-event times of
 profiled steps (youth_cuda_profile_*; A/B evidence, not a bench value).  One JSON line per library, flushed at once.
-    python tools/variant_probe.py [--frames 300] [--reps 5] [names ...]        (default: default s8d2mb5 s8d3mb4 s8d4mb4 d3mb4 d4mb3 d3mb4xy3 d4mb4xy3slim d5mb3xy3 d6mb3xy3 xy3 fastdiv)
+    python tools/variant_probe.py [--frames 300] [--reps 5] [names ...]        (default: the default library and every library under lib/variants/)
 """
 import argparse
 import ctypes as C
@@ -70,8 +70,13 @@ def main():
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--child", default=None)
-    ap.add_argument("names", nargs="*", default=["default", "s8d2mb5", "s8d3mb4", "s8d4mb4", "d3mb4", "d4mb3", "d3mb4xy3", "d4mb4xy3slim", "d5mb3xy3", "d6mb3xy3", "xy3", "fastdiv"])
+    ap.add_argument("names", nargs="*", default=None)
     args = ap.parse_args()
+    if args.names is None:
+        import glob
+
+        found = sorted(glob.glob(os.path.join(ROOT, "slam-rgbd_b200", "lib", "variants", "libyouth_cuda_*.so")))
+        args.names = ["default"] + [os.path.basename(f)[len("libyouth_cuda_"):-3] for f in found]
     if args.child:
         return child(args.child, args.frames, args.reps)
     import youth_pkg
