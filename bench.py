@@ -889,6 +889,7 @@ def run_ours(args):
         "frames_per_sec_per_gpu": main["value"] / world,
         "streaming_single_frame": streaming,
         "facade": facade,
+        "facade_zero_copy": (facade or {}).get("pinned_runs"),
         "packed_input": main.get("packed_input"),
         "extra_configs": extras or None,
     }
@@ -935,10 +936,20 @@ def facade_arm(pkg, args, local, frames, poses, ppt):
             host.youthSlamDrain()
             assert host.youthSlamGetTrajectory(fposes.ctypes.data, None, None, FRAMES) == FRAMES
 
+        # frames that already live in page-locked memory: no CPU copy at all (youthSlamProcessPinnedFrames)
+        nb = FRAMES * fb
+        pin = pkg.cuda_lib().youth_cuda_host_alloc(nb)
+        assert pin
+        C.memmove(pin, frames[0].ctypes.data, nb)
+        ts = np.arange(FRAMES, dtype=np.uint32) * 33
+
+        def pass_pinned():
+            host.resetSlam()
+            assert host.youthSlamProcessPinnedFrames(pin, FRAMES, W, H, ts.ctypes.data) == 1
+            assert host.youthSlamGetTrajectory(fposes.ctypes.data, None, None, FRAMES) == FRAMES
+
         fsteps = max(1, min(args.steps, 10))
-        for name, fn, check in (("processSlamFrame", pass_copy, True), ("zero_copy", pass_zero_copy, True)):
-            if name == "zero_copy" and not hasattr(host, "youthSlamAcquireSlot"):
-                continue
+        for name, fn in (("processSlamFrame", pass_copy), ("zero_copy_slot", pass_zero_copy), ("pinned_runs", pass_pinned)):
             for _ in range(2):
                 fn()
             t0 = time.perf_counter()
@@ -947,12 +958,16 @@ def facade_arm(pkg, args, local, frames, poses, ppt):
             fdt = time.perf_counter() - t0
             out[name] = {"frames_per_sec": FRAMES * fsteps / fdt, "steps": fsteps,
                          "bit_identical_to_device_arm": bool(np.array_equal(fposes.view(np.uint32), poses.view(np.uint32)))}
+        pkg.cuda_lib().youth_cuda_host_free(pin)
         out["frames_per_sec"] = out["processSlamFrame"]["frames_per_sec"]
         out["bit_identical_to_device_arm"] = out["processSlamFrame"]["bit_identical_to_device_arm"]
+        out["copy_threads"] = int(os.environ.get("YOUTH_SLAM_COPY_THREADS", "4"))
         out["what"] = (f"SLAM.h facade, lossless, {group} frames per launch group, two groups in flight.  processSlamFrame: "
-                       "one call per frame, the pageable host frame is copied into the pinned ring on the caller's thread "
-                       "(SLAM.cpp:133-134).  zero_copy: youthSlamAcquireSlot / youthSlamCommitSlot, the producer fills the "
-                       "ring slot itself (here: a memmove standing for chunk reassembly)")
+                       "one call per frame, the pageable host frame is copied into the pinned ring before the call returns "
+                       "(SLAM.cpp:133-134), the copy shared by copy_threads host threads.  zero_copy_slot: "
+                       "youthSlamAcquireSlot / youthSlamCommitSlot, the producer fills the ring slot itself (here: one "
+                       "single-threaded memmove per frame standing for chunk reassembly).  pinned_runs: "
+                       "youthSlamProcessPinnedFrames, the frames already live in page-locked memory and are read in place")
         host.stopSlamModule()
     except Exception as e:  # the facade arm is informative only
         out["error"] = f"{type(e).__name__}: {e}"

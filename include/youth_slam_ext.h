@@ -32,6 +32,11 @@ void youthSlamDrain(void);
 uint16_t* youthSlamAcquireSlot(int width, int height);
 int youthSlamCommitSlot(uint32_t timestamp_ms);
 
+/* n frames back to back that already live in page-locked host memory (youth_cuda_host_alloc): no CPU copy, the
+ * GPU's copy engine reads them in place, launch groups of the configured size, two in flight.  Ordered after
+ * everything queued before; synchronous (returns when the n frames are tracked). */
+int youthSlamProcessPinnedFrames(const uint16_t* frames, int n, int width, int height, const uint32_t* timestamps);
+
 /* Replay of FRAME_TYPE_DEPTH_PACKED records (include/youth_codec.h): n YD16 streams back to back, offsets[n+1]. */
 int youthSlamProcessPackedFrames(const uint8_t* streams, const uint64_t* offsets, int n, int width, int height,
                                  const uint32_t* timestamps);

@@ -102,6 +102,110 @@ static void copy_in(void* dst, const void* src, size_t bytes) {
 static void copy_in(void* dst, const void* src, size_t bytes) { memcpy(dst, src, bytes); }
 #endif
 
+/* Parallel copy-in.  One thread moves a VGA frame in ~50-60 us (13 GB/s of streaming stores), i.e. at most ~18 k
+ * frames/s through processSlamFrame() however fast the tracker is.  For replay and benchmarks (frames arriving back
+ * to back) a few helper threads share the copy: the caller's thread copies the first stripe and waits for the
+ * others, so the call is still synchronous (SLAM.cpp:133-134: the caller may reuse its buffer on return).  Helpers
+ * spin briefly for the next frame and then sleep on a condition variable, so a live 30 fps producer costs nothing
+ * between frames.  YOUTH_SLAM_COPY_THREADS = total threads per frame copy (default 4, 1 = off). */
+#define COPY_HELPERS_MAX 7
+#define COPY_MIN_BYTES (256u << 10) /* smaller frames are copied by the caller alone (YOUTH_SLAM_COPY_MIN_BYTES overrides) */
+static struct {
+  pthread_t th[COPY_HELPERS_MAX];
+  int n; /* helpers running */
+  pthread_mutex_t mu;
+  pthread_cond_t go;
+  atomic_ullong gen; /* job counter: a new value = a new job is posted */
+  atomic_int remaining;
+  atomic_int quit;
+  atomic_int sleepers;
+  const char* src;
+  char* dst;
+  size_t stripe, bytes, min_bytes;
+  unsigned long long gen0; /* value of gen when the helpers of this run of the module were started */
+} CP = {.mu = PTHREAD_MUTEX_INITIALIZER, .go = PTHREAD_COND_INITIALIZER};
+
+static void* copy_helper(void* arg) {
+  const int k = (int)(intptr_t)arg; /* stripe index 1 .. n */
+  unsigned long long seen = CP.gen0; /* jobs of an earlier run of the module are not ours */
+  for (;;) {
+    unsigned long long g = atomic_load_explicit(&CP.gen, memory_order_acquire);
+    int spins = 0;
+    while (g == seen && !atomic_load(&CP.quit)) {
+      if (++spins < 4000) {
+#if defined(__SSE2__)
+        _mm_pause();
+#endif
+      } else { /* ~50 us without a frame: sleep until the next one is posted */
+        pthread_mutex_lock(&CP.mu);
+        atomic_fetch_add(&CP.sleepers, 1);
+        while (atomic_load_explicit(&CP.gen, memory_order_acquire) == seen && !atomic_load(&CP.quit)) pthread_cond_wait(&CP.go, &CP.mu);
+        atomic_fetch_sub(&CP.sleepers, 1);
+        pthread_mutex_unlock(&CP.mu);
+        spins = 0;
+      }
+      g = atomic_load_explicit(&CP.gen, memory_order_acquire);
+    }
+    if (atomic_load(&CP.quit)) return NULL;
+    seen = g;
+    const size_t a = CP.stripe * (size_t)k;
+    if (a < CP.bytes) copy_in(CP.dst + a, CP.src + a, CP.bytes - a < CP.stripe ? CP.bytes - a : CP.stripe);
+    atomic_fetch_sub_explicit(&CP.remaining, 1, memory_order_release);
+  }
+}
+
+static void copy_pool_start(void) {
+  const char* e = getenv("YOUTH_SLAM_COPY_THREADS");
+  int want = e ? atoi(e) : 4;
+  if (want > COPY_HELPERS_MAX + 1) want = COPY_HELPERS_MAX + 1;
+  const char* mb = getenv("YOUTH_SLAM_COPY_MIN_BYTES");
+  CP.min_bytes = mb ? (size_t)atol(mb) : COPY_MIN_BYTES;
+  if (CP.min_bytes < 128) CP.min_bytes = 128;
+  atomic_store(&CP.quit, 0);
+  atomic_store(&CP.remaining, 0);
+  CP.gen0 = atomic_load(&CP.gen);
+  CP.n = 0;
+  for (int k = 1; k < want; ++k) {
+    if (pthread_create(&CP.th[CP.n], NULL, copy_helper, (void*)(intptr_t)k) != 0) break;
+    CP.n++;
+  }
+}
+
+static void copy_pool_stop(void) {
+  pthread_mutex_lock(&CP.mu);
+  atomic_store(&CP.quit, 1);
+  pthread_cond_broadcast(&CP.go);
+  pthread_mutex_unlock(&CP.mu);
+  for (int k = 0; k < CP.n; ++k) pthread_join(CP.th[k], NULL);
+  CP.n = 0;
+}
+
+/* one producer at a time gets here (the `filling` flag of the ring) */
+static void copy_in_parallel(void* dst, const void* src, size_t bytes) {
+  if (CP.n == 0 || bytes < CP.min_bytes) {
+    copy_in(dst, src, bytes);
+    return;
+  }
+  const size_t parts = (size_t)CP.n + 1;
+  CP.stripe = ((bytes + parts - 1) / parts + 63) & ~(size_t)63; /* whole cache lines, 16-byte aligned stripes */
+  CP.bytes = bytes;
+  CP.src = (const char*)src;
+  CP.dst = (char*)dst;
+  atomic_store_explicit(&CP.remaining, CP.n, memory_order_relaxed);
+  atomic_fetch_add_explicit(&CP.gen, 1, memory_order_release);
+  if (atomic_load(&CP.sleepers) > 0) {
+    pthread_mutex_lock(&CP.mu);
+    pthread_cond_broadcast(&CP.go);
+    pthread_mutex_unlock(&CP.mu);
+  }
+  copy_in(dst, src, CP.stripe < bytes ? CP.stripe : bytes);
+  while (atomic_load_explicit(&CP.remaining, memory_order_acquire) > 0) {
+#if defined(__SSE2__)
+    _mm_pause();
+#endif
+  }
+}
+
 /* A run of ring slots handed to the tracker and not collected yet.  The worker keeps up to two in
  * flight: it submits run g+1 (asynchronous youth_cuda_track_batch: its H2D copy runs on the copy stream
  * under the kernels of run g) before it waits for run g, publishes its poses and releases its slots.
@@ -296,7 +400,9 @@ void initSlamModule(const char* config_file, const char* vocabulary_file) {
   atomic_store(&G.last_inliers, 0);
   atomic_store(&G.stop_req, 0);
   atomic_store(&G.failed, 0);
+  copy_pool_start();
   if (pthread_create(&G.worker, NULL, worker_main, NULL) != 0) {
+    copy_pool_stop();
     fprintf(stderr, "AlgorithmModule: cannot start the worker thread\n");
     youth_cuda_host_free(G.ring);
     free(G.ts);
@@ -324,6 +430,7 @@ void stopSlamModule(void) {
   while (G.filling) pthread_cond_wait(&G.prod, &G.mu);
   pthread_mutex_unlock(&G.mu);
   pthread_join(G.worker, NULL); /* the worker drains what is queued before leaving */
+  copy_pool_stop();                 /* no producer holds a slot any more (waited for above) */
   /* a producer that passed the `running` test before stop_req was set either holds the mutex now (wait for it
    * to leave) or will see stop_req once it has it */
   pthread_mutex_lock(&G.mu);
@@ -438,7 +545,7 @@ int processSlamFrame(const int16_t* depth_data, const uint8_t* color_data, int w
   /* the synchronous copy of SLAM.cpp:133-134, outside the mutex: the caller may reuse its buffer on return.
    * reference depth is int16_t; values >= 32768 are reinterpreted as uint16 like the CV_16UC1 view at
    * SLAM.cpp:133 and then rejected by the depth_max gate */
-  copy_in(slot, depth_data, frame_px() * sizeof(uint16_t));
+  copy_in_parallel(slot, depth_data, frame_px() * sizeof(uint16_t));
   return youthSlamCommitSlot(timestamp);
 }
 
@@ -511,6 +618,78 @@ int youthSlamProcessPackedFrames(const uint8_t* streams, const uint64_t* offsets
   free(poses);
   free(status);
   return ok;
+}
+
+/* Frames that already live in page-locked host memory (youth_cuda_host_alloc: a recording loaded there, a producer
+ * whose own buffers are page-locked): no CPU copy at all -- the copy engine reads them where they are.  n frames
+ * back to back, tracked in launch groups of the configured size with two groups in flight, in order after
+ * everything queued through processSlamFrame().  Synchronous: returns when all n frames are tracked, so the caller
+ * may reuse the memory (the ownership rule of SLAM.cpp:133-134, at run granularity). */
+int youthSlamProcessPinnedFrames(const uint16_t* frames, int n, int width, int height, const uint32_t* timestamps) {
+  if (!atomic_load(&G.running) || !frames || n < 1 || atomic_load(&G.failed)) return 0;
+  if (width != G.cfg.width || height != G.cfg.height) return 0;
+  float* poses[2];
+  uint32_t* status[2];
+  int* inl[2];
+  for (int k = 0; k < 2; ++k) {
+    poses[k] = (float*)youth_cuda_host_alloc(sizeof(float) * 12 * (size_t)G.batch);
+    status[k] = (uint32_t*)youth_cuda_host_alloc(sizeof(uint32_t) * (size_t)G.batch);
+    inl[k] = (int*)youth_cuda_host_alloc(sizeof(int));
+  }
+  lock_idle(); /* the worker is idle and cannot claim frames while we hold the mutex: the handle is ours */
+  int ok = G.h != NULL && poses[0] && poses[1] && status[0] && status[1] && inl[0] && inl[1];
+  struct {
+    int valid, n, base, f0;
+    uint64_t ticket;
+  } pend = {0, 0, 0, 0, 0}, cur;
+  int turn = 0;
+  long sent = 0;
+  for (int f0 = 0; ok && (f0 < n || pend.valid); f0 += G.batch) {
+    memset(&cur, 0, sizeof(cur));
+    if (f0 < n) {
+      const int cn = n - f0 < G.batch ? n - f0 : G.batch;
+      const uint16_t* src[1] = {frames + frame_px() * (size_t)f0};
+      ok = youth_cuda_track_batch(G.h, src, cn, YOUTH_MEM_HOST_PINNED, timestamps ? timestamps + f0 : NULL, NULL);
+      cur.base = youth_cuda_frame_count(G.h, 0) - cn;
+      ok = ok && youth_cuda_read_last_inliers_async(G.h, 0, inl[turn]) &&
+           youth_cuda_read_trajectory_async(G.h, 0, cur.base, cn, poses[turn], status[turn], &cur.ticket) == cn;
+      cur.valid = ok;
+      cur.n = cn;
+      cur.f0 = f0;
+      turn ^= 1;
+    }
+    if (pend.valid) {
+      const int b = turn ^ (cur.valid ? 0 : 1); /* the buffer of the run submitted before `cur` */
+      ok = youth_cuda_wait_ticket(G.h, pend.ticket) && ok;
+      if (ok) {
+        atomic_store(&G.last_inliers, *inl[b]);
+        G.accepted += pend.n;
+        G.tracked += pend.n;
+        if (G.pose_mq != (mqd_t)-1) {
+          char msg[sizeof(MessageHeader) + sizeof(YouthPoseMsg)];
+          for (int i = 0; i < pend.n; ++i) {
+            const size_t len = youth_pose_msg_build(msg, pend.base + i, timestamps ? timestamps[pend.f0 + i] : 0u,
+                                                    poses[b] + 12 * (size_t)i, status[b][i], (uint32_t)*inl[b]);
+            if (mq_send(G.pose_mq, msg, len, 0) == 0) ++sent;
+          }
+        }
+      }
+    }
+    pend = cur;
+  }
+  if (!ok) {
+    fprintf(stderr, "AlgorithmModule: tracking failed: %s\n", youth_cuda_last_error());
+    if (G.h) youth_cuda_sync(G.h); /* nothing of the caller's memory is in flight when we return */
+    atomic_store(&G.failed, 1);
+  }
+  G.poses_sent += sent;
+  pthread_mutex_unlock(&G.mu);
+  for (int k = 0; k < 2; ++k) {
+    youth_cuda_host_free(poses[k]);
+    youth_cuda_host_free(status[k]);
+    youth_cuda_host_free(inl[k]);
+  }
+  return ok ? 1 : 0;
 }
 
 int youthSlamGetTrajectory(float* poses_out, uint32_t* timestamps_out, uint32_t* status_out, int max_frames) {

@@ -83,5 +83,9 @@ def chain(rel_poses):
 
 
 def rot_angle(Ra, Rb):
-    c = (np.trace(Ra.T @ Rb) - 1.0) / 2.0
-    return float(np.arccos(np.clip(c, -1.0, 1.0)))
+    """angle of Ra^T Rb from its skew part (sin) and trace (cos): well conditioned near zero, where arccos of the
+    trace alone turns a 1e-7 rounding of a matrix entry into 4e-4 rad"""
+    D = np.asarray(Ra, dtype=np.float64).T @ np.asarray(Rb, dtype=np.float64)
+    s = 0.5 * np.linalg.norm([D[2, 1] - D[1, 2], D[0, 2] - D[2, 0], D[1, 0] - D[0, 1]])
+    c = (np.trace(D) - 1.0) / 2.0
+    return float(np.arctan2(s, c))

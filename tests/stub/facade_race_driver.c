@@ -71,6 +71,7 @@ static void* reader(void* arg) {
 int main(int argc, char** argv) {
   if (argc < 3) return 2;
   setenv("YOUTH_STUB_DELAY_US", "100", 1);
+  setenv("YOUTH_SLAM_COPY_MIN_BYTES", "1024", 1); /* the 6 KB test frames go through the parallel copy-in too */
   for (int round = 0; round < 10; ++round) {
     const int lossless = round & 1;
     youthSlamSetOptions(lossless, 4);

@@ -45,6 +45,7 @@ def fut(tmp_path_factory):
     L.youthSlamAcquireSlot.restype = C.c_void_p
     L.youthSlamAcquireSlot.argtypes = [C.c_int, C.c_int]
     L.youthSlamCommitSlot.argtypes = [C.c_uint32]
+    L.youthSlamProcessPinnedFrames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     cfg = tmp_path_factory.mktemp("cfg") / "cam.yaml"
     cfg.write_text(f"%YAML:1.0\nCamera.width: {W}\nCamera.height: {H}\nCamera.fx: 57.03\nCamera.fy: 57.03\n"
                    "Camera.cx: 32.0\nCamera.cy: 24.0\nDepthMapFactor: 1000.0\n")
@@ -155,6 +156,37 @@ def test_zero_copy_producer_fills_ring_slots_in_place(fut, monkeypatch):
     assert fut.stub_torn_frames() == 0
     fut.stopSlamModule()
     assert not fut.youthSlamAcquireSlot(W, H)  # stopped
+
+
+def test_parallel_copy_in_and_pinned_runs(fut, monkeypatch):
+    """processSlamFrame with the copy shared by helper threads (forced for the small test frames), and
+    youthSlamProcessPinnedFrames (no copy: the tracker reads the caller's page-locked frames in place), interleaved:
+    every frame once, in order, whole (first and last pixel carry the marker)."""
+    monkeypatch.setenv("YOUTH_SLAM_COPY_MIN_BYTES", "256")
+    monkeypatch.setenv("YOUTH_SLAM_COPY_THREADS", "4")
+    fut.youthSlamSetOptions(1, 16)
+    fut.initSlamModule(fut.cfg_path, None)
+    marks, i = [], 1
+    for rnd in range(6):
+        for _ in range(25):
+            f = frame(i)
+            assert fut.processSlamFrame(f.ctypes.data, None, W, H, i) == 1
+            marks.append(i)
+            i += 1
+        run = np.stack([frame(i + k) for k in range(40)])
+        ts = np.arange(i, i + 40, dtype=np.uint32)
+        assert fut.youthSlamProcessPinnedFrames(run.ctypes.data, 40, W, H, ts.ctypes.data) == 1
+        marks += list(range(i, i + 40))
+        i += 40
+    fut.youthSlamDrain()
+    n = len(marks)
+    assert stats(fut) == (n, 0, n)
+    poses, ts = trajectory(fut, n)
+    assert list(poses[:, 3]) == marks and list(ts) == marks
+    assert fut.stub_torn_frames() == 0
+    assert fut.youthSlamProcessPinnedFrames(run.ctypes.data, 40, W + 8, H, None) == 0
+    fut.stopSlamModule()
+    assert fut.youthSlamProcessPinnedFrames(run.ctypes.data, 40, W, H, None) == 0
 
 
 def test_tracker_failure_is_sticky_until_reset(fut, monkeypatch):
