@@ -155,6 +155,16 @@ int youth_cuda_last_inliers(youth_cuda_handle* h, int stream);
  * zero-copy hand-off to a collective (NCCL gather of per-sequence trajectories). */
 void* youth_cuda_trajectory_device_ptr(youth_cuda_handle* h, int stream);
 
+/* Device helpers for C hosts that do not link the CUDA runtime themselves (host/multi_gpu.c gives these buffers
+ * to NCCL): device count, current device of the calling thread, device memory, blocking copy to the host, and a
+ * whole-device synchronisation. */
+int youth_cuda_device_count(void);
+int youth_cuda_set_device(int device);
+void* youth_cuda_device_alloc(size_t bytes);
+void youth_cuda_device_free(void* p);
+int youth_cuda_copy_to_host(void* dst, const void* src_device, size_t bytes);
+int youth_cuda_device_sync(void);
+
 /* Page-locked host memory for YOUTH_MEM_HOST_PINNED inputs. */
 void* youth_cuda_host_alloc(size_t bytes);
 void youth_cuda_host_free(void* p);

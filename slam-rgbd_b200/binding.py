@@ -131,6 +131,12 @@ def cuda_lib():
         "youth_cuda_read_last_inliers_async": (C.c_int, [H, C.c_int, C.c_void_p]),
         "youth_cuda_last_inliers": (C.c_int, [H, C.c_int]),
         "youth_cuda_trajectory_device_ptr": (C.c_void_p, [H, C.c_int]),
+        "youth_cuda_device_count": (C.c_int, []),
+        "youth_cuda_set_device": (C.c_int, [C.c_int]),
+        "youth_cuda_device_alloc": (C.c_void_p, [C.c_size_t]),
+        "youth_cuda_device_free": (None, [C.c_void_p]),
+        "youth_cuda_copy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+        "youth_cuda_device_sync": (C.c_int, []),
         "youth_cuda_host_alloc": (C.c_void_p, [C.c_size_t]),
         "youth_cuda_host_free": (None, [C.c_void_p]),
         "youth_cuda_debug_enable_maps": (C.c_int, [H]),

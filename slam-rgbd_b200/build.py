@@ -15,6 +15,6 @@ def build_all(verbose: bool = False) -> None:
         print(res.stderr)
     if res.returncode != 0:
         raise RuntimeError("native build failed (see output above)")
-    for rel in ("lib/libyouth_cuda.so", "lib/libAlgorithmModule.so", "bin/youth_harness"):
+    for rel in ("lib/libyouth_cuda.so", "lib/libAlgorithmModule.so", "lib/libyouth_synth.so", "bin/youth_harness", "bin/youth_multi"):
         if not os.path.exists(os.path.join(PKG_DIR, rel)):
             raise RuntimeError(f"native build did not produce {rel}")

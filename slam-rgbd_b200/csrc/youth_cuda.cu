@@ -1449,6 +1449,41 @@ extern "C" void youth_cuda_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 
+/* Device helpers for C hosts that do not link the CUDA runtime themselves (the native multi-GPU harness hands
+ * these buffers to NCCL). */
+extern "C" int youth_cuda_device_count(void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
+extern "C" int youth_cuda_set_device(int device) {
+  CU(cudaSetDevice(device));
+  return 1;
+}
+
+extern "C" void* youth_cuda_device_alloc(size_t bytes) {
+  void* p = NULL;
+  if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+    fail("cudaMalloc of %zu bytes failed", bytes);
+    return NULL;
+  }
+  return p;
+}
+
+extern "C" void youth_cuda_device_free(void* p) {
+  if (p) cudaFree(p);
+}
+
+extern "C" int youth_cuda_copy_to_host(void* dst, const void* src_device, size_t bytes) {
+  CU(cudaMemcpy(dst, src_device, bytes, cudaMemcpyDeviceToHost));
+  return 1;
+}
+
+extern "C" int youth_cuda_device_sync(void) {
+  CU(cudaDeviceSynchronize());
+  return 1;
+}
+
 /* ------------------------------------------------------------------ parity hooks */
 
 static int slot_of_frame(const youth_cuda_handle* h, int frame) {

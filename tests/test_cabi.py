@@ -49,7 +49,7 @@ def test_facade_library_exports_reference_entry_points(pkg):
     # exactly the reference's exported C symbols (SLAM.h:11-38, algorithmModule.h:6)
     assert sorted(facade) == sorted(["initSlamModule", "stopSlamModule", "processSlamFrame", "saveSlamMap",
                                      "isSlamModuleRunning", "getSlamMapPoints", "resetSlam", "algorithmModule"])
-    for n in facade + declared_functions("youth_host.h"):
+    for n in facade + declared_functions("youth_host.h") + declared_functions("youth_slam_ext.h"):
         assert hasattr(lib, n), f"libAlgorithmModule.so does not export {n}"
 
 
