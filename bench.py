@@ -611,7 +611,7 @@ def measure(ctx, Wd, Hd, levels, S, batch, ppt, steps, warmup, label="", full=Fa
     # ---- packed-input arm: the same step fed from YD16 streams (include/youth_codec.h) in pinned host memory; the
     # packed bytes cross PCIe and are unpacked on the device.  Pipelined like e2e (two steps in flight): with
     # several GPUs behind one host memory system this is the feed that keeps the host side out of the way.
-    if (full or world > 1) and not args.no_packed and mode != "model":
+    if (full or (world > 1 and (Wd, Hd) == (W, H))) and not args.no_packed and mode != "model":
         cd = pkg.Codec(Wd, Hd, max_frames=FRAMES, device=local)
         enc = [cd.encode_ptr(d_base + k * seq_bytes, FRAMES, B.MEM_DEVICE) for k in range(S)]
         enc_ms = cd.last_kernel_ms()

@@ -8,6 +8,9 @@
  */
 #include "youth_common.cuh"
 
+#ifndef YK_INGEST_MIN_BLOCKS
+#define YK_INGEST_MIN_BLOCKS 6 /* resident k_ingest CTAs per SM the register budget is sized for (40 registers, 35 KB smem) */
+#endif
 #define YK_TILE_W 64
 #define YK_TILE_H 16
 #define YK_HALO 3
@@ -173,6 +176,63 @@ __device__ __forceinline__ float2 bilateral_pair_wt(const float (*tile)[YK_SMEM_
   return make_float2(c.x != YK_SENTINEL ? swd.x / sw.x : 0.0f, c.y != YK_SENTINEL ? swd.y / sw.y : 0.0f);
 }
 
+/* The same for TWO vertically adjacent pixel pairs, rows y and y + 1 of the tile: their 7-row windows share six of
+ * eight rows, so every window row is loaded once (five LDS.64) and feeds both -- row R of the eight is window row
+ * dy = R of the upper pair and dy = R - 1 of the lower pair.  Each pixel still sees its 49 taps in row-major order
+ * (the order of the specification); only the interleaving between the four pixels changes.  40 instead of 70 row
+ * loads per four pixels: shared-memory wavefronts are this kernel's tightest resource (ncu: ~90 % of the LSU
+ * data-pipe peak), the table lookups are one per tap either way. */
+template <int R>
+__device__ __forceinline__ void bilateral_row2(const float (*tile)[YK_SMEM_W], int xo, int y, float2 negcA, float2 negcB,
+                                               float cutf, float2 ulp4, float2 lbase, float2& swA, float2& swdA, float2& swB,
+                                               float2& swdB) {
+  const float2* row = reinterpret_cast<const float2*>(&tile[y + R][xo + 4]);
+  const float2 t0 = row[0], t1 = row[1], t2 = row[2], t3 = row[3], t4 = row[4];
+  if (R <= 6) {
+    constexpr int DY = R <= 6 ? R : 0;
+    bilateral_col<DY, 0>(t0.y, negcA, cutf, ulp4, lbase, swA, swdA);
+    bilateral_col<DY, 1>(t1.x, negcA, cutf, ulp4, lbase, swA, swdA);
+    bilateral_col<DY, 2>(t1.y, negcA, cutf, ulp4, lbase, swA, swdA);
+    bilateral_col<DY, 3>(t2.x, negcA, cutf, ulp4, lbase, swA, swdA);
+    bilateral_col<DY, 4>(t2.y, negcA, cutf, ulp4, lbase, swA, swdA);
+    bilateral_col<DY, 5>(t3.x, negcA, cutf, ulp4, lbase, swA, swdA);
+    bilateral_col<DY, 6>(t3.y, negcA, cutf, ulp4, lbase, swA, swdA);
+    bilateral_col<DY, 7>(t4.x, negcA, cutf, ulp4, lbase, swA, swdA);
+  }
+  if (R >= 1) {
+    constexpr int DY = R >= 1 ? R - 1 : 0;
+    bilateral_col<DY, 0>(t0.y, negcB, cutf, ulp4, lbase, swB, swdB);
+    bilateral_col<DY, 1>(t1.x, negcB, cutf, ulp4, lbase, swB, swdB);
+    bilateral_col<DY, 2>(t1.y, negcB, cutf, ulp4, lbase, swB, swdB);
+    bilateral_col<DY, 3>(t2.x, negcB, cutf, ulp4, lbase, swB, swdB);
+    bilateral_col<DY, 4>(t2.y, negcB, cutf, ulp4, lbase, swB, swdB);
+    bilateral_col<DY, 5>(t3.x, negcB, cutf, ulp4, lbase, swB, swdB);
+    bilateral_col<DY, 6>(t3.y, negcB, cutf, ulp4, lbase, swB, swdB);
+    bilateral_col<DY, 7>(t4.x, negcB, cutf, ulp4, lbase, swB, swdB);
+  }
+}
+
+/* rows y and y + 1: .x/.y of dA are the pixels (xo, y), (xo+1, y); dB the same one row down */
+__device__ __forceinline__ void bilateral_quad_wt(const float (*tile)[YK_SMEM_W], const float* s_wt, float cutf, int xo, int y,
+                                                  float2& dA, float2& dB) {
+  const float2 cA = make_float2(tile[y + YK_HALO][xo + 8], tile[y + YK_HALO][xo + 9]);
+  const float2 cB = make_float2(tile[y + 1 + YK_HALO][xo + 8], tile[y + 1 + YK_HALO][xo + 9]);
+  float2 swA = make_float2(0.0f, 0.0f), swdA = swA, swB = swA, swdB = swA;
+  const float2 negcA = make_float2(-cA.x, -cA.y), negcB = make_float2(-cB.x, -cB.y);
+  const float ulp = __int_as_float(4), lb = __int_as_float((int)__cvta_generic_to_shared(s_wt));
+  const float2 ulp4 = make_float2(ulp, ulp), lbase = make_float2(lb, lb);
+  bilateral_row2<0>(tile, xo, y, negcA, negcB, cutf, ulp4, lbase, swA, swdA, swB, swdB);
+  bilateral_row2<1>(tile, xo, y, negcA, negcB, cutf, ulp4, lbase, swA, swdA, swB, swdB);
+  bilateral_row2<2>(tile, xo, y, negcA, negcB, cutf, ulp4, lbase, swA, swdA, swB, swdB);
+  bilateral_row2<3>(tile, xo, y, negcA, negcB, cutf, ulp4, lbase, swA, swdA, swB, swdB);
+  bilateral_row2<4>(tile, xo, y, negcA, negcB, cutf, ulp4, lbase, swA, swdA, swB, swdB);
+  bilateral_row2<5>(tile, xo, y, negcA, negcB, cutf, ulp4, lbase, swA, swdA, swB, swdB);
+  bilateral_row2<6>(tile, xo, y, negcA, negcB, cutf, ulp4, lbase, swA, swdA, swB, swdB);
+  bilateral_row2<7>(tile, xo, y, negcA, negcB, cutf, ulp4, lbase, swA, swdA, swB, swdB);
+  dA = make_float2(cA.x != YK_SENTINEL ? swdA.x / swA.x : 0.0f, cA.y != YK_SENTINEL ? swdA.y / swA.y : 0.0f);
+  dB = make_float2(cB.x != YK_SENTINEL ? swdB.x / swB.x : 0.0f, cB.y != YK_SENTINEL ? swdB.y / swB.y : 0.0f);
+}
+
 #define YK_D0_W (YK_TILE_W + 4) /* level-0 depth tile with the +1 halo column/row the normals need (66 used) */
 #define YK_D0_H (YK_TILE_H + 1)
 
@@ -180,10 +240,10 @@ __device__ __forceinline__ float2 bilateral_pair_wt(const float (*tile)[YK_SMEM_
  * DBG: also store the filtered float depth pyramid and the pyramid sample counts -- nothing on the product path reads
  * them (0.5 GB per 300 frames and 485 MB per handle saved); parity read-back and the model ray cast's depth hint do. */
 template <int MODE, bool FD, bool DBG>
-__global__ void __launch_bounds__(256) k_ingest(const __grid_constant__ IngestParams P) {
+__global__ void __launch_bounds__(256, YK_INGEST_MIN_BLOCKS) k_ingest(const __grid_constant__ IngestParams P) {
   constexpr bool BILATERAL = MODE != YK_INGEST_RAW;
   __shared__ __align__(16) float tile[YK_SMEM_H][YK_SMEM_W];
-  __shared__ float d0s[YK_D0_H][YK_D0_W];
+  __shared__ __align__(8) float d0s[YK_D0_H][YK_D0_W];
   /* 65 columns used; the pitch of 66 keeps every row 16-byte (vxy) / 8-byte (vz) aligned, so the normals pass
    * reads a pixel pair with one 128-bit / 64-bit load instead of stride-2 64-bit / 32-bit loads (which cost two
    * wavefronts per ideal one: 15 % of this kernel's shared-memory wavefronts, its tightest resource) */
@@ -245,8 +305,17 @@ __global__ void __launch_bounds__(256) k_ingest(const __grid_constant__ IngestPa
   /* level-0 depth: work items are pixel pairs (xo, xo+1); 32 x 16 items cover the tile, 49 more
    * cover the halo row y = 16 and the halo column pair (64, 65) */
   const float cutf = (float)(P.range_cut + 1);
+  if (MODE == YK_INGEST_BILATERAL_WT) {
+    /* the tile proper in ONE pass: every thread filters a 2 x 2 block (two pixel pairs in rows 2w, 2w + 1 of warp w);
+     * the window rows the two rows share are loaded once */
+    const int xo = 2 * (tid & 31), y = 2 * (tid >> 5);
+    float2 dA, dB;
+    bilateral_quad_wt(tile, s_wr, cutf, xo, y, dA, dB);
+    *reinterpret_cast<float2*>(&d0s[y][xo]) = dA;
+    *reinterpret_cast<float2*>(&d0s[y + 1][xo]) = dB;
+  }
 #pragma unroll 1
-  for (int pass = 0; pass < 3; ++pass) {
+  for (int pass = (MODE == YK_INGEST_BILATERAL_WT ? 2 : 0); pass < 3; ++pass) {
     int xo, y;
     if (pass < 2) {
       xo = 2 * (tid & 31);

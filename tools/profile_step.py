@@ -31,7 +31,8 @@ def main():
 
     n = args.batch * args.groups
     cfg = pkg.default_config(batch=args.batch, n_streams=args.streams, width=args.width, height=args.height,
-                             levels=args.levels, icp_ppt=args.ppt, traj_capacity=max(n, 1),
+                             levels=args.levels, iters=[10, 5, 4, 4][:args.levels] + [0] * (4 - args.levels),
+                             icp_ppt=args.ppt, traj_capacity=max(n, 1),
                              fx=570.3 * args.width / 640, fy=570.3 * args.width / 640, cx=args.width / 2,
                              cy=args.height / 2)
     trk = B.Tracker(cfg)

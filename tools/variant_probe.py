@@ -72,7 +72,7 @@ def main():
     ap.add_argument("--child", default=None)
     ap.add_argument("names", nargs="*", default=None)
     args = ap.parse_args()
-    if args.names is None:
+    if not args.names:
         import glob
 
         found = sorted(glob.glob(os.path.join(ROOT, "slam-rgbd_b200", "lib", "variants", "libyouth_cuda_*.so")))
