@@ -5,7 +5,7 @@ bench.py uses, together with the SHA-1 of the CUDA sources the captures were tak
 only while that still matches).
 
   python tools/make_traffic.py <commit> <geom_key>=<report.ncu-rep> [...]
-  e.g. 640x480_L3_S1_B300_ppt128_frame=gpurun_out/r2h_main.ncu-rep
+  e.g. 640x480_L3_S1_B300_ppt128_frame=gpurun_out/r2h_main_raw.csv
 Also writes profiles/<report>_summary.csv (the selected metrics of every captured launch) next to it."""
 import csv
 import io
@@ -20,7 +20,10 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 
 def launches(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):  # the raw page exported on the GPU box (tools/ncu_round.sh)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     head, units = rows[0], rows[1]
     out = []
@@ -72,8 +75,8 @@ def main():
             u = d["_units"]
             b = to_bytes(d["dram__bytes_read.sum"], u["dram__bytes_read.sum"]) + to_bytes(d["dram__bytes_write.sum"], u["dram__bytes_write.sum"])
             per.setdefault(cls, []).append(b)
-        name = os.path.splitext(os.path.basename(rep))[0]
-        summary = os.path.join("profiles", name + "_summary.csv")
+        name = os.path.splitext(os.path.basename(rep))[0].replace("_raw", "")
+        summary = os.path.join("profiles", name + "_ncu_full_summary.csv")
         ncu_summarize.full(rep, os.path.join(ROOT, summary))
         captures[key] = {"source": summary + " (ncu --set full --clock-control none of tools/profile_step.py, one launch group)",
                          "dram_bytes_per_launch": {k: sum(v) / len(v) for k, v in per.items()},

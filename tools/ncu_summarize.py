@@ -36,7 +36,10 @@ FULL_METRICS = [
 
 
 def full(rep, out):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):  # already the raw page (exported on the GPU box)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     cols = ["Kernel Name", "Grid Size", "Block Size"] + [m for m in FULL_METRICS if m in hdr]
