@@ -41,6 +41,11 @@ int youth_bin_write_eof(FILE* f);
  * color may be NULL (payload skipped). */
 int youth_bin_read_frame(FILE* f, FrameHeader* hdr, void* depth, size_t depth_cap, void* color,
                          size_t color_cap);
+/* the same in two steps, for a reader that picks the destination after it has seen the header (e.g. a slot of the
+ * tracker's page-locked frame ring, include/youth_slam_ext.h): header (0 at end of file / EOF marker), then the
+ * payloads of that header */
+int youth_bin_read_header(FILE* f, FrameHeader* hdr);
+int youth_bin_read_payload(FILE* f, const FrameHeader* hdr, void* depth, size_t depth_cap, void* color, size_t color_cap);
 
 /* ---------------------------------------------------------------- mq chunk protocol */
 /* number of MAX_MSG_SIZE messages needed for `bytes` of payload */

@@ -31,6 +31,7 @@ void youthSlamDrain(void);
  * frame was queued. */
 uint16_t* youthSlamAcquireSlot(int width, int height);
 int youthSlamCommitSlot(uint32_t timestamp_ms);
+void youthSlamAbortSlot(void); /* give the acquired slot back unpublished (the frame could not be completed) */
 
 /* n frames back to back that already live in page-locked host memory (youth_cuda_host_alloc): no CPU copy, the
  * GPU's copy engine reads them in place, launch groups of the configured size, two in flight.  Ordered after

@@ -226,6 +226,7 @@ def host_lib():
         "youthSlamStats": (None, [C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_long)]),
         "youthSlamAcquireSlot": (C.c_void_p, [C.c_int, C.c_int]),
         "youthSlamCommitSlot": (C.c_int, [C.c_uint32]),
+        "youthSlamAbortSlot": (None, []),
         "youthSlamProcessPinnedFrames": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     }
     for name, (res, args) in sig.items():

@@ -59,7 +59,22 @@ void* algorithmModule(void* id) {
   uint64_t offs[PACKED_RUN + 1] = {0};
   uint32_t ts[PACKED_RUN];
   int nrun = 0, rw = 0, rh = 0, failed = 0;
-  while (depth && !failed && youth_bin_read_frame(f, &hdr, depth, cap, NULL, 0)) {
+  while (depth && !failed && youth_bin_read_header(f, &hdr)) {
+    if (hdr.frameType != FRAME_TYPE_DEPTH_PACKED && nrun == 0 &&
+        (size_t)hdr.depthDataSize == (size_t)hdr.width * hdr.height * 2) {
+      /* a raw frame: read it straight into a slot of the tracker's page-locked ring (no second copy) */
+      uint16_t* slot = youthSlamAcquireSlot(hdr.width, hdr.height);
+      if (slot) {
+        if (!youth_bin_read_payload(f, &hdr, slot, (size_t)hdr.depthDataSize, NULL, 0)) {
+          youthSlamAbortSlot(); /* a torn record: nothing is published */
+          break;
+        }
+        if (!youthSlamCommitSlot(hdr.timestamp)) break;
+        ++frames;
+        continue;
+      }
+    }
+    if (!youth_bin_read_payload(f, &hdr, depth, cap, NULL, 0)) break;
     if (hdr.frameType == FRAME_TYPE_DEPTH_PACKED) {
       if (offs[nrun] + hdr.depthDataSize > run_cap) {
         run_cap = 2 * (offs[nrun] + hdr.depthDataSize) + (1u << 20);

@@ -521,6 +521,16 @@ int youthSlamCommitSlot(uint32_t timestamp) {
   return ok;
 }
 
+/* Give the slot of the last youthSlamAcquireSlot() back unpublished (the producer could not complete the frame). */
+void youthSlamAbortSlot(void) {
+  pthread_mutex_lock(&G.mu);
+  if (G.filling) {
+    G.filling = 0;
+    pthread_cond_broadcast(&G.prod);
+  }
+  pthread_mutex_unlock(&G.mu);
+}
+
 int processSlamFrame(const int16_t* depth_data, const uint8_t* color_data, int width, int height, uint32_t timestamp) {
   (void)color_data; /* depth-only tracker; colour passes through the pipeline untouched */
   if (!depth_data) return 0;

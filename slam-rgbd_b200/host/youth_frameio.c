@@ -74,11 +74,14 @@ int youth_bin_write_eof(FILE* f) {
   return fwrite(&h, sizeof(h), 1, f) == 1;
 }
 
-int youth_bin_read_frame(FILE* f, FrameHeader* hdr, void* depth, size_t depth_cap, void* color,
-                         size_t color_cap) {
-  if (!f || !hdr || !depth) return 0;
+int youth_bin_read_header(FILE* f, FrameHeader* hdr) {
+  if (!f || !hdr) return 0;
   if (fread(hdr, sizeof(*hdr), 1, f) != 1) return 0;
-  if (hdr->frameType == FRAME_TYPE_END_OF_FILE) return 0;
+  return hdr->frameType != FRAME_TYPE_END_OF_FILE;
+}
+
+int youth_bin_read_payload(FILE* f, const FrameHeader* hdr, void* depth, size_t depth_cap, void* color, size_t color_cap) {
+  if (!f || !hdr || !depth) return 0;
   if (hdr->depthDataSize > depth_cap) return 0;
   if (color && hdr->colorDataSize > color_cap) return 0;
   if (fread(depth, 1, hdr->depthDataSize, f) != hdr->depthDataSize) return 0;
@@ -88,6 +91,12 @@ int youth_bin_read_frame(FILE* f, FrameHeader* hdr, void* depth, size_t depth_ca
     if (fseek(f, (long)hdr->colorDataSize, SEEK_CUR) != 0) return 0;
   }
   return 1;
+}
+
+int youth_bin_read_frame(FILE* f, FrameHeader* hdr, void* depth, size_t depth_cap, void* color,
+                         size_t color_cap) {
+  if (!depth) return 0;
+  return youth_bin_read_header(f, hdr) && youth_bin_read_payload(f, hdr, depth, depth_cap, color, color_cap);
 }
 
 /* ------------------------------------------------------------------ chunks */

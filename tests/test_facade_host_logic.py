@@ -136,6 +136,9 @@ def test_zero_copy_producer_fills_ring_slots_in_place(fut, monkeypatch):
     fut.youthSlamSetOptions(1, 96)
     fut.initSlamModule(fut.cfg_path, None)
     assert fut.youthSlamCommitSlot(0) == 0  # nothing acquired
+    assert fut.youthSlamAcquireSlot(W, H)
+    fut.youthSlamAbortSlot()  # given back unpublished: nothing is tracked, the next acquire gets the same slot
+    assert fut.youthSlamCommitSlot(0) == 0
     assert not fut.youthSlamAcquireSlot(W + 8, H)  # not the configured size
     n = 400
     for i in range(1, n + 1):
