@@ -611,16 +611,28 @@ def measure(ctx, Wd, Hd, levels, S, batch, ppt, steps, warmup, label="", full=Fa
     # ---- packed-input arm: the same step fed from YD16 streams (include/youth_codec.h) in pinned host memory; the
     # packed bytes cross PCIe and are unpacked on the device.  Pipelined like e2e (two steps in flight): with
     # several GPUs behind one host memory system this is the feed that keeps the host side out of the way.
-    if (full or (world > 1 and (Wd, Hd) == (W, H))) and not args.no_packed and mode != "model":
-        cd = pkg.Codec(Wd, Hd, max_frames=FRAMES, device=local)
-        enc = [cd.encode_ptr(d_base + k * seq_bytes, FRAMES, B.MEM_DEVICE) for k in range(S)]
-        enc_ms = cd.last_kernel_ms()
-        back = torch.empty(FRAMES * Wd * Hd, dtype=torch.int16, device=f"cuda:{local}")
-        cd.decode_to_device(enc[0][0], enc[0][1], back.data_ptr())
-        dec_ms = cd.last_kernel_ms()
-        codec_ok = bool(torch.equal(back.view(FRAMES, Hd, Wd), d_frames[0]))
-        del back
-        cd.close()
+    want_packed = (full or (world > 1 and (Wd, Hd) == (W, H))) and not args.no_packed and mode != "model"
+    enc = None
+    if want_packed:
+        # the set-up (encoding the step's frames once) is local work: if it fails on ANY rank every rank skips the
+        # arm -- the timed part below contains collectives, and the headline arms above must not be lost to it
+        why = ""
+        try:
+            cd = pkg.Codec(Wd, Hd, max_frames=FRAMES, device=local)
+            enc = [cd.encode_ptr(d_base + k * seq_bytes, FRAMES, B.MEM_DEVICE) for k in range(S)]
+            enc_ms = cd.last_kernel_ms()
+            back = torch.empty(FRAMES * Wd * Hd, dtype=torch.int16, device=f"cuda:{local}")
+            cd.decode_to_device(enc[0][0], enc[0][1], back.data_ptr())
+            dec_ms = cd.last_kernel_ms()
+            codec_ok = bool(torch.equal(back.view(FRAMES, Hd, Wd), d_frames[0]))
+            del back
+            cd.close()
+        except Exception as e:
+            enc, why = None, f"{type(e).__name__}: {e}"
+        if max_over_ranks(0.0 if enc is not None else 1.0) > 0.0:
+            out["packed_input"] = {"error": why or "set-up failed on another rank", "what": "YD16 packed-input arm skipped"}
+            enc = None
+    if enc is not None:
         pk_bytes = [int(e[1][-1]) for e in enc]
         pk_pin = [trk.lib.youth_cuda_host_alloc(b) for b in pk_bytes]
         for ptr, e in zip(pk_pin, enc):
