@@ -88,10 +88,13 @@ def measured_peak():
 
 
 def kernels_sha1():
-    """Identity of the device code: SHA-1 over the CUDA sources.  profiles/traffic.json carries the value its ncu
-    capture was taken with; a capture of other kernels is not reported as this run's traffic."""
+    """Identity of the device code: SHA-1 over the CUDA sources that hold kernels (everything under csrc/ except
+    youth_cuda.cu, which is host code: the C ABI).  profiles/traffic.json carries the value its ncu capture was taken
+    with; a capture of other kernels is not reported as this run's traffic."""
     h = hashlib.sha1()
     for p in sorted(glob.glob(os.path.join(ROOT, "slam-rgbd_b200", "csrc", "*.cu*"))):
+        if os.path.basename(p) == "youth_cuda.cu":
+            continue
         h.update(os.path.basename(p).encode())
         with open(p, "rb") as f:
             h.update(f.read())

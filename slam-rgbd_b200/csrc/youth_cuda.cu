@@ -454,7 +454,15 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
     CU(cudaMalloc((void**)&d_bad, sizeof(bad)));
     CU(cudaMemset(d_bad, 0, sizeof(bad)));
     h->r_df = 1.0f / df;
-    if (ok) yk_launch_div_check(df, h->r_df, d_bad);
+    float checked[1 + 2 * YOUTH_MAX_LEVELS]; /* every distinct divisor is checked once (fx == fy for the Astra) */
+    int n_checked = 0;
+    auto check_once = [&](float b, float r) {
+      for (int k = 0; k < n_checked; ++k)
+        if (checked[k] == b) return;
+      checked[n_checked++] = b;
+      yk_launch_div_check(b, r, d_bad);
+    };
+    if (ok) check_once(df, h->r_df);
     for (int l = 0; l < cfg->levels; ++l) {
       const LevelGeom& g = h->lv[l];
       ok = ok && g.fx >= 0x1p-10f && g.fx <= 0x1p20f && g.fy >= 0x1p-10f && g.fy <= 0x1p20f &&
@@ -463,8 +471,8 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
       h->r_fx[l] = 1.0f / g.fx;
       h->r_fy[l] = 1.0f / g.fy;
       if (ok) {
-        yk_launch_div_check(g.fx, h->r_fx[l], d_bad);
-        yk_launch_div_check(g.fy, h->r_fy[l], d_bad);
+        check_once(g.fx, h->r_fx[l]);
+        check_once(g.fy, h->r_fy[l]);
       }
     }
     CU(cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost));
