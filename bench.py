@@ -672,7 +672,7 @@ def measure(ctx, Wd, Hd, levels, S, batch, ppt, steps, warmup, label="", full=Fa
 
         run_packed(warmup)
         barrier()
-        psteps = max(2, min(steps, 20))
+        psteps = steps if world > 1 else max(2, min(steps, 20))
         t0 = time.perf_counter()
         run_packed(psteps)
         trk.sync()
@@ -826,6 +826,12 @@ def run_ours(args):
         xs = max(3, min(args.steps, 8))
         r3 = measure(ctx, W, H, 3, 8, 300, 128, xs, 3, label="configs3.")
         extras["configs3"] = dict(slim(r3), config=config_dict(W, H, 3, 8, 300, 128, world), steps=xs, warmup=3, clocks=None)
+        pk3 = r3.get("packed_input") or {}
+        if world > 1 and "e2e_value" in pk3 and pk3.get("bit_identical_to_device_arm"):
+            extras["configs3"]["e2e_raw_frames"] = extras["configs3"]["e2e"]
+            extras["configs3"]["e2e"] = {"value": pk3["e2e_value"], "unit": "frames/s", "h2d_bytes_per_step": pk3["h2d_bytes_per_step"],
+                                         "d2h_bytes_per_step": pk3["d2h_bytes_per_step"], "bit_identical_to_device_arm": True,
+                                         "input": "YD16-packed host frames, unpacked on the device"}
         del r3
         r4 = measure(ctx, 1280, 960, 4, 1, 300, 128, xs, 3, label="configs4.")
         extras["configs4"] = dict(slim(r4), config=config_dict(1280, 960, 4, 1, 300, 128, world), steps=xs, warmup=3,
@@ -877,12 +883,27 @@ def run_ours(args):
         cpu1_fps, _, _ = cpu_sample(frames[0], ocfg, 1, 4, tsdf_cfg=mt)
         cpu1p_fps = cpu1_fps
     else:
+        cpu_sample(frames[0], ocfg, threads, 3)  # untimed: first touch of the oracle's buffers, library load
         cpu_fps, cpu_wall, cpu_kind = cpu_sample(frames[0], ocfg, threads, fpt)
         cpu1_fps, _, _ = cpu_sample(frames[0], ocfg, 1, 6)               # one thread, speed build
         cpu1p_fps, _, _ = cpu_sample(frames[0], ocfg, 1, 6, fast=False)  # one thread, parity build
         if not args.no_parity:
             parity = parity_check(ctx, main, min(FRAMES, args.parity_frames))
 
+    # Several GPUs behind one host memory system: raw frames cost 184 MB of H2D per GPU and step, and eight ranks
+    # copying at once are bound by the host side (round 1: 0.963 scaling efficiency end to end).  With more than
+    # one rank the end-to-end feed is therefore the YD16-packed host input (a third of the bytes, unpacked on the
+    # device inside the timed region, bit-identical frames and trajectory); the raw-frame number stays in the line
+    # as e2e_raw_frames.  One rank: raw frames (packed_input reports the packed feed).
+    e2e_line = main["e2e"]
+    pk = main.get("packed_input") or {}
+    if world > 1 and "e2e_value" in pk and pk.get("bit_identical_to_device_arm"):
+        e2e_line = {"value": pk["e2e_value"], "unit": "frames/s", "h2d_bytes_per_step": pk["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": pk["d2h_bytes_per_step"], "bit_identical_to_device_arm": True,
+                    "steps_in_flight": 2, "steps": pk["steps"],
+                    "input": "YD16-packed host frames (lossless, include/youth_codec.h), unpacked on the device",
+                    "how": "youth_cuda_track_batch_packed (pinned host streams) + youth_cuda_read_trajectory_async per step, "
+                           "youth_cuda_wait_ticket of the step before; H2D, unpacking and D2H of every step inside the timed region"}
     line = {
         "metric": "icp_tracked_frames_per_sec", "value": main["value"], "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
@@ -890,7 +911,8 @@ def run_ours(args):
         "config": config_dict(Wd, Hd, args.levels, S, args.batch, ppt, world, args.mode),
         "host_placement": placement,
         "clocks": clocks,
-        "e2e": main["e2e"],
+        "e2e": e2e_line,
+        "e2e_raw_frames": main["e2e"] if e2e_line is not main["e2e"] else None,
         "e2e_blocking": main.get("e2e_blocking"),
         "gpu_launches": main["launches"],
         "roofline": main["roofline"],
