@@ -159,6 +159,7 @@ void* youth_cuda_trajectory_device_ptr(youth_cuda_handle* h, int stream);
  * to NCCL): device count, current device of the calling thread, device memory, blocking copy to the host, and a
  * whole-device synchronisation. */
 int youth_cuda_device_count(void);
+void* youth_cuda_stream(youth_cuda_handle* h); /* cudaStream_t the handle launches on (for stream-ordered collectives) */
 int youth_cuda_set_device(int device);
 void* youth_cuda_device_alloc(size_t bytes);
 void youth_cuda_device_free(void* p);

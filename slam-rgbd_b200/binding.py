@@ -132,6 +132,7 @@ def cuda_lib():
         "youth_cuda_last_inliers": (C.c_int, [H, C.c_int]),
         "youth_cuda_trajectory_device_ptr": (C.c_void_p, [H, C.c_int]),
         "youth_cuda_device_count": (C.c_int, []),
+        "youth_cuda_stream": (C.c_void_p, [H]),
         "youth_cuda_set_device": (C.c_int, [C.c_int]),
         "youth_cuda_device_alloc": (C.c_void_p, [C.c_size_t]),
         "youth_cuda_device_free": (None, [C.c_void_p]),

@@ -1469,6 +1469,10 @@ extern "C" int youth_cuda_set_device(int device) {
   return 1;
 }
 
+/* the stream the handle launches on: work enqueued there by the caller (a collective on the trajectories) is
+ * ordered after everything submitted so far, with no host synchronisation */
+extern "C" void* youth_cuda_stream(youth_cuda_handle* h) { return h ? (void*)h->stream : NULL; }
+
 extern "C" void* youth_cuda_device_alloc(size_t bytes) {
   void* p = NULL;
   if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
