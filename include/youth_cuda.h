@@ -164,6 +164,7 @@ int youth_cuda_set_device(int device);
 void* youth_cuda_device_alloc(size_t bytes);
 void youth_cuda_device_free(void* p);
 int youth_cuda_copy_to_host(void* dst, const void* src_device, size_t bytes);
+int youth_cuda_copy_to_device(void* dst_device, const void* src, size_t bytes);
 int youth_cuda_device_sync(void);
 
 /* Page-locked host memory for YOUTH_MEM_HOST_PINNED inputs. */

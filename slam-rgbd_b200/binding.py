@@ -137,6 +137,7 @@ def cuda_lib():
         "youth_cuda_device_alloc": (C.c_void_p, [C.c_size_t]),
         "youth_cuda_device_free": (None, [C.c_void_p]),
         "youth_cuda_copy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+        "youth_cuda_copy_to_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
         "youth_cuda_device_sync": (C.c_int, []),
         "youth_cuda_host_alloc": (C.c_void_p, [C.c_size_t]),
         "youth_cuda_host_free": (None, [C.c_void_p]),

@@ -313,6 +313,15 @@ extern "C" void youth_cuda_destroy(youth_cuda_handle* h) {
   delete h;
 }
 
+/* Page-locked staging for pageable input (YOUTH_MEM_HOST): 2 x P frames.  Callers that only ever hand over
+ * page-locked or device memory (the facade's ring, bench.py, the multi-GPU driver) never pin it. */
+static int ensure_staging(youth_cuda_handle* h) {
+  const size_t bytes = (size_t)h->P * h->cfg.width * h->cfg.height * sizeof(uint16_t);
+  for (int k = 0; k < 2; ++k)
+    if (!h->pinned[k]) CU(cudaHostAlloc((void**)&h->pinned[k], bytes, cudaHostAllocDefault));
+  return 1;
+}
+
 /* buffers + kernel instantiation for the float depth pyramid and the pyramid sample counts (parity read-back, model
  * ray-cast hint).  Cached graphs were captured with the instantiation that does not store them: drop them. */
 static int ensure_debug_maps(youth_cuda_handle* h) {
@@ -410,7 +419,7 @@ static int init_impl(const youth_cuda_config* cfg, youth_cuda_handle* h) {
   const size_t frame_px = (size_t)cfg->width * cfg->height;
   for (int k = 0; k < 2; ++k) {
     CU(dalloc(&h->raw[k], (size_t)h->P * frame_px));
-    CU(cudaHostAlloc((void**)&h->pinned[k], (size_t)h->P * frame_px * sizeof(uint16_t), cudaHostAllocDefault));
+    h->pinned[k] = NULL; /* staging for pageable input: page-locked on first YOUTH_MEM_HOST call (ensure_staging) */
     CU(cudaEventCreateWithFlags(&h->raw_free[k], cudaEventDisableTiming));
     for (int c2 = 0; c2 < YK_MAX_CHUNKS; ++c2) CU(cudaEventCreateWithFlags(&h->chunk_ready[k][c2], cudaEventDisableTiming));
   }
@@ -1117,6 +1126,7 @@ extern "C" int youth_cuda_track_batch(youth_cuda_handle* h, const uint16_t* cons
     const int k = h->raw_turn;
     h->raw_turn ^= 1;
     /* the landing zone may still be read by the group launched two calls ago */
+    if (mem_kind == YOUTH_MEM_HOST && !ensure_staging(h)) return 0;
     if (h->raw_used[k]) {
       if (mem_kind == YOUTH_MEM_HOST)
         CU(cudaEventSynchronize(h->raw_free[k])); /* the pinned staging copy is about to be overwritten */
@@ -1446,7 +1456,8 @@ extern "C" void* youth_cuda_trajectory_device_ptr(youth_cuda_handle* h, int stre
 
 extern "C" void* youth_cuda_host_alloc(size_t bytes) {
   void* p = NULL;
-  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+  /* portable: page-locked for every device of the process (a multi-GPU host pins once, any handle may read it) */
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
     fail("cudaHostAlloc(%zu) failed", bytes);
     return NULL;
   }
@@ -1488,6 +1499,11 @@ extern "C" void youth_cuda_device_free(void* p) {
 
 extern "C" int youth_cuda_copy_to_host(void* dst, const void* src_device, size_t bytes) {
   CU(cudaMemcpy(dst, src_device, bytes, cudaMemcpyDeviceToHost));
+  return 1;
+}
+
+extern "C" int youth_cuda_copy_to_device(void* dst_device, const void* src, size_t bytes) {
+  CU(cudaMemcpy(dst_device, src, bytes, cudaMemcpyHostToDevice));
   return 1;
 }
 

@@ -6,8 +6,9 @@
  *
  * The path shards over independent sequences only: GPU g tracks sequences
  * g*S .. g*S+S-1 (seed 20261018 + sequence) from page-locked host frames, the S sequences of a GPU in the same
- * launches.  No collective inside the data path; ONE ncclAllGather per step hands every GPU all trajectories
- * (G x S x frames x 12 floats, zero-copy from youth_cuda_trajectory_device_ptr).  Thread 0 then writes one TUM file
+ * launches.  No collective inside the data path; ONE ncclAllGather at the end of the run hands every GPU all
+ * trajectories (G x S x frames x 12 floats, zero-copy from youth_cuda_trajectory_device_ptr, ordered behind the last
+ * step on the handle's own stream).  Thread 0 then writes one TUM file
  * per sequence, <out_prefix>_seq<NNN>_trajectory.txt, from ITS copy of the gathered buffer -- so the files of the
  * sequences tracked on other GPUs prove the gather.  Timing: every thread meets a barrier, tracks `steps` steps,
  * synchronises its device and meets a barrier again; the wall clock between the barriers is the max over GPUs.
@@ -72,12 +73,22 @@ static void* rank_main(void* arg) {
     if (!frames || !gathered) failed = 1;
   }
   const uint16_t* ptrs[64];
+  /* The trajectories are gathered ONCE, behind the last step (one collective at the end of a
+   * run; a "step" re-tracks the same sequences for timing).  YOUTH_MULTI_GATHER_EVERY_STEP=1 gathers behind every
+   * step instead; YOUTH_MULTI_DEVICE_INPUT=1 tracks from a device-resident copy of the frames (no H2D in the loop). */
+  const int no_gather = getenv("YOUTH_MULTI_GATHER_EVERY_STEP") == NULL, dev_input = getenv("YOUTH_MULTI_DEVICE_INPUT") != NULL;
+  uint16_t* dframes = NULL;
   if (!failed) {
     for (int k = 0; k < r->S; ++k) {
       youth_synth_config sc;
       youth_synth_default(&sc, r->w, r->h, r->g * r->S + k);
       youth_synth_sequence(&sc, 0, r->n, frames + fpx * (size_t)r->n * k);
       ptrs[k] = frames + fpx * (size_t)r->n * k;
+    }
+    if (dev_input) {
+      dframes = (uint16_t*)youth_cuda_device_alloc(fpx * 2 * (size_t)r->S * r->n);
+      if (!dframes || !youth_cuda_copy_to_device(dframes, frames, fpx * 2 * (size_t)r->S * r->n)) failed = 1;
+      for (int k = 0; k < r->S; ++k) ptrs[k] = dframes + fpx * (size_t)r->n * k;
     }
   }
   /* every rank reaches the barriers and the collective whether or not it failed locally: nobody is left waiting */
@@ -88,10 +99,14 @@ static void* rank_main(void* arg) {
      * handle's copy stream under the kernels of the step before), and the one collective -- the per-sequence
      * trajectories of every GPU -- is ordered behind the step on the handle's own stream */
     if (!failed) {
-      if (!youth_cuda_reset(h, -1) || !youth_cuda_track_batch(h, ptrs, r->n, YOUTH_MEM_HOST_PINNED, NULL, NULL)) failed = 1;
+      if (!youth_cuda_reset(h, -1) ||
+          !youth_cuda_track_batch(h, ptrs, r->n, dev_input ? YOUTH_MEM_DEVICE : YOUTH_MEM_HOST_PINNED, NULL, NULL))
+        failed = 1;
     }
-    const void* send = (failed || !h) ? (const void*)gathered : youth_cuda_trajectory_device_ptr(h, 0);
-    if (ncclAllGather(send, gathered, traj_floats, ncclFloat, r->comm, h ? (cudaStream_t)youth_cuda_stream(h) : NULL) != ncclSuccess) failed = 1;
+    if (!no_gather || s == r->steps - 1) {
+      const void* send = (failed || !h) ? (const void*)gathered : youth_cuda_trajectory_device_ptr(h, 0);
+      if (ncclAllGather(send, gathered, traj_floats, ncclFloat, r->comm, h ? (cudaStream_t)youth_cuda_stream(h) : NULL) != ncclSuccess) failed = 1;
+    }
   }
   if (h && !youth_cuda_sync(h)) failed = 1;
   if (!youth_cuda_device_sync()) failed = 1;
@@ -112,6 +127,7 @@ static void* rank_main(void* arg) {
   }
   free(host);
   youth_cuda_device_free(gathered);
+  youth_cuda_device_free(dframes);
   youth_cuda_host_free(frames);
   youth_cuda_destroy(h);
   r->ok = !failed;
@@ -131,6 +147,8 @@ int main(int argc, char** argv) {
     fprintf(stderr, "youth_multi: %d GPUs wanted, %d visible (no CPU fallback)\n", G, youth_cuda_device_count());
     return 1;
   }
+  /* threads of one process: every device launches the collective on its own, with no cross-device launch group */
+  setenv("NCCL_LAUNCH_MODE", "PARALLEL", 0);
   ncclComm_t comms[16];
   int devs[16];
   for (int g = 0; g < G; ++g) devs[g] = g;
@@ -164,8 +182,8 @@ int main(int argc, char** argv) {
   if (!ok) return 1;
   const double secs = ranks[0].seconds;
   printf("{\"gpus\": %d, \"sequences_per_gpu\": %d, \"frames_per_sequence\": %d, \"steps\": %d, \"seconds\": %.6f, "
-         "\"frames_per_sec\": %.1f, \"what\": \"one pthread + one tracker handle per GPU, pinned host frames in, one stream-ordered ncclAllGather "
-         "of the trajectories per step, no host synchronisation between steps (H2D and the gather inside the timed region)\", \"trajectories\": \"%s_seq<NNN>_trajectory.txt\"}\n",
+         "\"frames_per_sec\": %.1f, \"what\": \"one pthread + one tracker handle per GPU, pinned host frames in, no host synchronisation between steps, one "
+         "stream-ordered ncclAllGather of the trajectories behind the last step (H2D and the gather inside the timed region)\", \"trajectories\": \"%s_seq<NNN>_trajectory.txt\"}\n",
          G, S, n, steps, secs, (double)G * S * n * steps / secs, argv[4]);
   return 0;
 }
