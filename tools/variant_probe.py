@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 SHM = "/dev/shm/youth_variant_probe_frames.npy"
 
 
-def child(name, frames_n, reps):
+def child(name, frames_n, reps, w=640, h=480, levels=3):
     t0 = time.time()
     import youth_pkg
 
@@ -30,10 +30,14 @@ def child(name, frames_n, reps):
     from slam_rgbd_b200 import binding as B
 
     frames = np.load(SHM, mmap_mode="r")
-    cfg = pkg.default_config(batch=frames_n, icp_ppt=128, traj_capacity=frames_n)
+    extra = {}
+    if (w, h) != (640, 480):
+        extra = dict(width=w, height=h, fx=570.3 * w / 640, fy=570.3 * w / 640, cx=w / 2.0, cy=h / 2.0)
+    cfg = pkg.default_config(batch=frames_n, icp_ppt=128, traj_capacity=frames_n, levels=levels,
+                             iters=[10, 5, 4, 4][:levels] + [0] * (4 - levels), **extra)
     trk = B.Tracker(cfg)
     lib = trk.lib
-    nbytes = frames_n * 480 * 640 * 2
+    nbytes = frames_n * h * w * 2
     pinned = lib.youth_cuda_host_alloc(nbytes)
     assert pinned
     C.memmove(pinned, frames.ctypes.data if hasattr(frames, "ctypes") else np.ascontiguousarray(frames).ctypes.data, nbytes)
@@ -56,7 +60,7 @@ def child(name, frames_n, reps):
         walls.append((time.time() - t1) * 1e3)
     ms, n = trk.profile_read()
     trk.profile(False)
-    names = {0: "k_ingest", 1: "k_normals", 2: "k_icp_L0", 3: "k_icp_L1", 4: "k_icp_L2", 7: "k_compose"}
+    names = {0: "k_ingest", 1: "k_normals", 2: "k_icp_L0", 3: "k_icp_L1", 4: "k_icp_L2", 5: "k_icp_L3", 7: "k_compose"}
     per = {names[k]: round(float(ms[k]) / reps, 4) for k in names if n[k]}
     print(json.dumps({"lib": name, "frames": frames_n, "trajectory_sha1": sha, "lost": int((st & 2 != 0).sum()),
                       "ms_per_step_by_kernel": per, "sum_ms": round(sum(per.values()), 4),
@@ -70,6 +74,9 @@ def main():
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--child", default=None)
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--levels", type=int, default=3)
     ap.add_argument("names", nargs="*", default=None)
     args = ap.parse_args()
     if not args.names:
@@ -78,11 +85,11 @@ def main():
         found = sorted(glob.glob(os.path.join(ROOT, "slam-rgbd_b200", "lib", "variants", "libyouth_cuda_*.so")))
         args.names = ["default"] + [os.path.basename(f)[len("libyouth_cuda_"):-3] for f in found]
     if args.child:
-        return child(args.child, args.frames, args.reps)
+        return child(args.child, args.frames, args.reps, args.width, args.height, args.levels)
     import youth_pkg
 
     pkg = youth_pkg.load()
-    np.save(SHM, pkg.synth_sequence(args.frames))
+    np.save(SHM, pkg.synth_sequence(args.frames, args.width, args.height))
     vdir = os.path.join(ROOT, "slam-rgbd_b200", "lib", "variants")
     for name in args.names:
         env = dict(os.environ)
@@ -94,7 +101,8 @@ def main():
                 continue
             env["YOUTH_CUDA_LIB"] = so
         res = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", name, "--frames", str(args.frames),
-                              "--reps", str(args.reps)], env=env, capture_output=True, text=True)
+                              "--reps", str(args.reps), "--width", str(args.width), "--height", str(args.height),
+                              "--levels", str(args.levels)], env=env, capture_output=True, text=True)
         sys.stdout.write(res.stdout)
         if res.returncode != 0:
             print(json.dumps({"lib": name, "error": res.stderr[-600:]}), flush=True)
