@@ -83,8 +83,9 @@ typedef struct {
 #define MSG_TYPE_POSE 5
 typedef struct {
   float pose[12];   /* camera-to-world, row-major 3x4 [R|t], world = first camera frame */
-  uint32_t status;  /* YOUTH_STATUS_* bits */
-  uint32_t inliers; /* correspondences of the last ICP iteration at the finest level */
+  uint32_t status;  /* the frame's own YOUTH_STATUS_* bits (FIRST = 1: origin of a sequence, LOST = 2: pose not updated) */
+  uint32_t inliers; /* correspondences of the last ICP iteration at the finest level, of the LAST frame of the launch
+                       group this frame was tracked in (the tracker keeps one count per sequence) */
 } YouthPoseMsg;
 
 #define YOUTH_CHUNK_PAYLOAD ((int)(MAX_MSG_SIZE - sizeof(MessageHeader))) /* 7900 */

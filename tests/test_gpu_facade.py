@@ -265,11 +265,15 @@ def test_pose_egress_to_viewer_queue(pkg, small_seq):
         out = np.zeros(14, dtype=np.uint32)
         fid, ts = C.c_int(), C.c_uint32()
         assert host.youth_pose_msg_parse(buf.ctypes.data, n, C.byref(fid), C.byref(ts), out.ctypes.data) == 1
-        got.append((fid.value, ts.value, out[:12].view(np.float32).copy()))
+        got.append((fid.value, ts.value, out[:12].view(np.float32).copy(), int(out[12]), int(out[13])))
     rt.mq_close(mq)
     rt.mq_unlink(name)
     assert [g[0] for g in got] == list(range(6)) and [g[1] for g in got] == [33 * i for i in range(6)]
     assert all(np.array_equal(g[2], poses[i]) for i, g in enumerate(got))
+    # status = the frame's own YOUTH_STATUS_* word (the first frame of a sequence is FIRST, tracked frames 0),
+    # inliers = the inlier count of the launch group's last frame (> 0 for tracked groups)
+    assert [g[3] for g in got] == [1, 0, 0, 0, 0, 0]
+    assert all(g[4] > 100000 for g in got)
 
 
 def test_golden_fixture_through_cabi(pkg):
