@@ -87,3 +87,46 @@ def test_our_arm_has_no_cpu_fallback():
     r = run_bench("--steps", "1", "--warmup", "0")
     assert r.returncode != 0 and r.stdout.strip() == ""
     assert "no CPU fallback" in r.stderr
+
+
+def test_roofline_arithmetic_is_reproducible_by_hand(monkeypatch):
+    """roofline.frac = compulsory DRAM bytes per launch / CUDA-event launch time / measured peak, with 299 pairs
+    (300 frames touched) per 300-frame launch; the 48 B/px/iteration the kernel requests is reported beside it; the
+    ncu traffic is only attached for the geometry AND the kernel sources it was captured with."""
+    import numpy as np
+
+    import bench
+
+    class B:  # the profiling class ids of slam-rgbd_b200/binding.py
+        PROF_INGEST, PROF_NORMALS, PROF_ICP0, PROF_SOLVE, PROF_MISC, PROF_RAYCAST, PROF_CLASSES = 0, 1, 2, 6, 7, 8, 9
+
+    ms = np.zeros(9)
+    n = np.zeros(9, dtype=np.int64)
+    ms[B.PROF_ICP0], n[B.PROF_ICP0] = 5.0, 10       # 0.5 ms per level-0 launch
+    ms[B.PROF_ICP0 + 1], n[B.PROF_ICP0 + 1] = 0.75, 5
+    ms[B.PROF_INGEST], n[B.PROF_INGEST] = 1.8, 1
+    ms[B.PROF_NORMALS], n[B.PROF_NORMALS] = 0.25, 1
+    monkeypatch.setattr(bench, "measured_peak", lambda: (6547.5, "measured (test)"))
+    out = bench.rooflines(B, ms, n, 640, 480, 3, 1, [(0, 300)], 300, 128, "frame")
+    top = out["roofline"]
+    comp = 24 * 640 * 480 * 300  # every frame of the group once
+    assert top["compulsory_bytes_per_launch"] == comp and top["pairs_per_launch"] == 299
+    assert top["requested_bytes_per_launch"] == 48 * 640 * 480 * 299
+    assert abs(top["frac"] - comp / 0.5e-3 / 1e9 / 6547.5) < 1e-12 and 0.6 < top["frac"] < 0.72
+    assert top["frac"] <= 1.0 and top["peak"] == 6547.5 and top["bound"] == "hbm"
+    kinds = [r["kernel"] for r in out["roofline_all"]]
+    assert kinds == ["k_icp (level 0)", "k_icp (level 1)", "k_ingest + k_normals"]
+    ing = out["roofline_all"][-1]
+    b_pre = 2 * 640 * 480 + 24 * (640 * 480 + 320 * 240 + 160 * 120)
+    assert ing["algorithmic_bytes_per_frame"] == b_pre and abs(ing["achieved"] - b_pre * 300 / 2.05e-3 / 1e9) < 1e-6
+    # two groups of 150: 149 + 150 pairs, 150 + 151 frames touched
+    out2 = bench.rooflines(B, ms, n, 640, 480, 3, 1, [(0, 150), (150, 150)], 150, 128, "frame")
+    assert out2["roofline"]["pairs_per_launch"] == 149.5
+    assert out2["roofline"]["compulsory_bytes_per_launch"] == 24 * 640 * 480 * 150.5
+    # traffic: attached for the captured geometry, refused when the kernel sources differ
+    t, src = bench.load_traffic("640x480_L3_S1_B300_ppt128_frame")
+    assert t.get("k_icp_L0", 0) > 2.2e9 and "captured at" in src
+    assert bench.load_traffic("641x480_L3_S1_B300_ppt128_frame")[0] == {}
+    monkeypatch.setattr(bench, "kernels_sha1", lambda: "0" * 40)
+    t, src = bench.load_traffic("640x480_L3_S1_B300_ppt128_frame")
+    assert t == {} and "other kernel sources" in src
