@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 SHM = "/dev/shm/youth_variant_probe_frames.npy"
 
 
-def child(name, frames_n, reps, w=640, h=480, levels=3):
+def child(name, frames_n, reps, w=640, h=480, levels=3, min_inliers=0):
     t0 = time.time()
     import youth_pkg
 
@@ -35,6 +35,8 @@ def child(name, frames_n, reps, w=640, h=480, levels=3):
         extra = dict(width=w, height=h, fx=570.3 * w / 640, fy=570.3 * w / 640, cx=w / 2.0, cy=h / 2.0)
     cfg = pkg.default_config(batch=frames_n, icp_ppt=128, traj_capacity=frames_n, levels=levels,
                              iters=[10, 5, 4, 4][:levels] + [0] * (4 - levels), **extra)
+    if min_inliers:
+        cfg.min_inliers = min_inliers  # timing experiments: no iteration updates the pose (identity association)
     trk = B.Tracker(cfg)
     lib = trk.lib
     nbytes = frames_n * h * w * 2
@@ -77,6 +79,7 @@ def main():
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--levels", type=int, default=3)
+    ap.add_argument("--min-inliers", type=int, default=0)
     ap.add_argument("names", nargs="*", default=None)
     args = ap.parse_args()
     if not args.names:
@@ -85,7 +88,7 @@ def main():
         found = sorted(glob.glob(os.path.join(ROOT, "slam-rgbd_b200", "lib", "variants", "libyouth_cuda_*.so")))
         args.names = ["default"] + [os.path.basename(f)[len("libyouth_cuda_"):-3] for f in found]
     if args.child:
-        return child(args.child, args.frames, args.reps, args.width, args.height, args.levels)
+        return child(args.child, args.frames, args.reps, args.width, args.height, args.levels, args.min_inliers)
     import youth_pkg
 
     pkg = youth_pkg.load()
@@ -102,7 +105,7 @@ def main():
             env["YOUTH_CUDA_LIB"] = so
         res = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", name, "--frames", str(args.frames),
                               "--reps", str(args.reps), "--width", str(args.width), "--height", str(args.height),
-                              "--levels", str(args.levels)], env=env, capture_output=True, text=True)
+                              "--levels", str(args.levels), "--min-inliers", str(args.min_inliers)], env=env, capture_output=True, text=True)
         sys.stdout.write(res.stdout)
         if res.returncode != 0:
             print(json.dumps({"lib": name, "error": res.stderr[-600:]}), flush=True)
