@@ -139,7 +139,8 @@ static void* copy_helper(void* arg) {
       } else { /* ~50 us without a frame: sleep until the next one is posted */
         pthread_mutex_lock(&CP.mu);
         atomic_fetch_add(&CP.sleepers, 1);
-        while (atomic_load_explicit(&CP.gen, memory_order_acquire) == seen && !atomic_load(&CP.quit)) pthread_cond_wait(&CP.go, &CP.mu);
+        /* sleepers++ then gen (both seq_cst) against the poster's gen++ then sleepers: one of the two sees the other */
+        while (atomic_load(&CP.gen) == seen && !atomic_load(&CP.quit)) pthread_cond_wait(&CP.go, &CP.mu);
         atomic_fetch_sub(&CP.sleepers, 1);
         pthread_mutex_unlock(&CP.mu);
         spins = 0;
@@ -192,7 +193,7 @@ static void copy_in_parallel(void* dst, const void* src, size_t bytes) {
   CP.src = (const char*)src;
   CP.dst = (char*)dst;
   atomic_store_explicit(&CP.remaining, CP.n, memory_order_relaxed);
-  atomic_fetch_add_explicit(&CP.gen, 1, memory_order_release);
+  atomic_fetch_add(&CP.gen, 1); /* seq_cst: publishes the job, and orders against the sleepers test below */
   if (atomic_load(&CP.sleepers) > 0) {
     pthread_mutex_lock(&CP.mu);
     pthread_cond_broadcast(&CP.go);
